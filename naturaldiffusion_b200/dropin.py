@@ -1,0 +1,116 @@
+"""Function-level drop-ins with the reference's exact signatures.
+
+The three reference scripts resolve ``weighted_sum`` / ``data_fn`` / ``euler_weighted_sum`` as module
+globals at call time, so ``install(module)`` (or plain attribute assignment) swaps the implementation
+without editing the scripts:
+
+    import CIFAR10NaturalInference as ref
+    import naturaldiffusion_b200.dropin as ni
+    ni.install(ref)            # ref.weighted_sum, ref.data_fn now launch libni_b200 kernels
+    ref.natural_inference_tx()
+
+Each call is one ``ni_weighted_sum`` launch (two for ``euler_weighted_sum``).  Inputs must be CUDA
+tensors; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import NiError
+from .ops import weighted_sum_tensors
+
+
+def _row_form(row, seq: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``weighted_sum(past_x0_coeff_row, seq_x0)`` of src/CIFAR10NaturalInference.py:233-238 and
+    ``weighted_sum(weights, seq_elem)`` of src/ValidateNaturalInference.py:198-204: float32 result.
+    Exact-zero coefficients are not read at all (the reference multiplies them; same values)."""
+    n = len(seq)
+    coeffs = [float(row[i]) for i in range(n)]
+    keep = [i for i in range(n) if coeffs[i] != 0.0]
+    if not keep:
+        return torch.zeros_like(seq[0], dtype=torch.float32)
+    return weighted_sum_tensors([coeffs[i] for i in keep], [seq[i] for i in keep], out_dtype=torch.float32)
+
+
+_sd3_memo = {"key": None, "val": None}
+
+
+def _sd3_form(seq: Sequence[torch.Tensor], weights=None, memoise: bool = True) -> torch.Tensor:
+    """``weighted_sum(seq_xstarts, weights=None)`` of src/SD3NaturalInference.py:157-168: row len(seq)-1,
+    normalised by its sum; result in the tensors' dtype (fp32 accumulate instead of the reference's fp16).
+    The SD3 loop calls it twice with identical arguments (:221 then :207 of the next step); the second call
+    returns the memoised tensor."""
+    n = len(seq)
+    if n == 0:
+        raise NiError("weighted_sum of an empty sequence")
+    w = [1.0] * n if weights is None else [float(weights[n - 1][i]) for i in range(n)]
+    key = (n, tuple(t.data_ptr() for t in seq), tuple(w))
+    if memoise and _sd3_memo["key"] == key:
+        return _sd3_memo["val"]
+    tot = float(sum(w))
+    keep = [i for i in range(n) if w[i] != 0.0]
+    if not keep:
+        out = torch.zeros_like(seq[0]) / tot
+    else:
+        out = weighted_sum_tensors([w[i] for i in keep], [seq[i] for i in keep], scale=1.0 / tot)
+    if memoise:
+        _sd3_memo["key"], _sd3_memo["val"] = key, out
+    return out
+
+
+def weighted_sum(a, b=None):
+    """Drop-in for all three reference ``weighted_sum`` functions; dispatches on the argument order:
+    (coefficient row, list of tensors) -> CIFAR / Validate form, (list of tensors, table|None) -> SD3 form."""
+    if isinstance(a, (list, tuple)) and (len(a) == 0 or isinstance(a[0], torch.Tensor)):
+        return _sd3_form(a, b)
+    return _row_form(a, b)
+
+
+_scalar_cache = {}
+
+
+def _as_float(w) -> float:
+    if isinstance(w, torch.Tensor):
+        k = (w.data_ptr(), w._version)
+        if k not in _scalar_cache:
+            if len(_scalar_cache) > 4096:
+                _scalar_cache.clear()
+            _scalar_cache[k] = float(w.item())  # one sync per NEW device scalar (the reference prints .item() per step anyway)
+        return _scalar_cache[k]
+    return float(w)
+
+
+def euler_weighted_sum(seq_xstarts: List, cliplen: int = 0):
+    """src/SD3NaturalInference.py:61-69: seq of [weight, tensor]; returns (sum w x, sum w x / sum w)."""
+    part = seq_xstarts[-cliplen:]
+    ws = [_as_float(w) for w, _ in part]
+    xs = [x for _, x in part]
+    acc = weighted_sum_tensors(ws, xs)
+    equiv = weighted_sum_tensors([1.0 / float(sum(ws))], [acc])
+    return acc, equiv
+
+
+@torch.no_grad()
+def data_fn(score_fn, xt, t, x_coeff, eps_coeff, device=None):
+    """src/CIFAR10NaturalInference.py:219-230: pred_x0 = (score*sigma^2 + xt)/alpha.  The reference returns
+    fp64; this returns fp32 (downstream only sums it, and `weighted_sum` casts to fp32 anyway) and does not
+    create per-step device scalars (the two blocking H2D copies at :226-227 disappear)."""
+    vec_t = t * torch.ones(xt.shape[0], device=xt.device)
+    score = score_fn(xt, vec_t)
+    alpha, sigma = float(x_coeff), float(eps_coeff)
+    if score.dtype != xt.dtype:
+        score = score.to(xt.dtype)
+    return weighted_sum_tensors([1.0 / alpha, sigma * sigma / alpha], [xt.contiguous(), score.contiguous()], out_dtype=torch.float32)
+
+
+def install(module) -> List[str]:
+    """Replace the hot-path functions of an imported reference script module; returns what was patched."""
+    patched = []
+    for name, fn in (("weighted_sum", weighted_sum), ("euler_weighted_sum", euler_weighted_sum), ("data_fn", data_fn)):
+        if hasattr(module, name):
+            setattr(module, name, fn)
+            patched.append(name)
+    return patched

@@ -1,0 +1,268 @@
+"""The Natural Inference sampler loop (loop-level drop-in).
+
+What the three reference loops do per step (src/CIFAR10NaturalInference.py:294-304,
+src/ValidateNaturalInference.py:349-366, src/SD3NaturalInference.py:201-221) becomes ONE
+``ni_step`` launch per step here: model I/O scaling + CFG, append-to-history, the row of A
+against the x0 ring, the row of B against stored noise and the freshly drawn noise.
+
+The python lists ``seq_x0`` / ``seq_eps`` / ``seq_xstarts`` of the reference (unbounded, fp64 for
+CIFAR) become a ring of fixed device slots sized from the liveness of the matrix columns
+(coeffs.build_plan): 4 slots for step_10_weight_42, 5 for step_15_weight_173, 14 for the sharp SD3
+table, K for dense first-order rows.
+
+Denoiser protocol: ``denoiser(x, k) -> out`` or ``(out0, out1)``; tensors of shape [B, C', H, W] with
+C' >= C (only the first C channels are read -- DiT's learned-sigma half is skipped without a copy).
+The denoiser stays torch (north-star); adapters for the reference's three model interfaces are in
+``naturaldiffusion_b200.adapters``.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NI_BF16, NI_MAX_TERMS, NiError
+from .coeffs import CoeffTriple, StepPlan, build_plan
+from .ops import DTYPE_CODE, StepLaunch, philox_normal, stream_ptr, to_pixel_u8
+
+
+class NaturalInferenceSampler:
+    def __init__(self, triple: CoeffTriple, io_scaling: Sequence[Tuple[float, float, float]], batch: int,
+                 sample_shape: Sequence[int], *, device="cuda", dtype: torch.dtype = torch.float32, seed: int = 0,
+                 eps0: str = "stored", lp_dtype: Optional[torch.dtype] = None, track_sumsq: bool = False,
+                 sample_offset: int = 0, keep_all_x0: bool = False):
+        """
+        triple       coefficient matrices (A, B, node)
+        io_scaling   K tuples (a_k, b0_k, b1_k): x0_k = a_k x_k + b0_k out0 + b1_k out1 (coeffs.io_*)
+        batch        samples on THIS rank; sample_offset = global index of its first sample, so the
+                     Philox noise of a sharded run equals the single-GPU run
+        eps0         "stored": the initial noise lives in a slot and is re-read by every row that uses it
+                     "regen" : rows regenerate it in-kernel from (seed, tensor 0) -- no slot, no reads
+        lp_dtype     also emit x_{k+1} in fp16/bf16 for a reduced-precision denoiser (fp32 state only)
+        """
+        if eps0 not in ("stored", "regen"):
+            raise NiError("eps0 must be 'stored' or 'regen'")
+        if dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise NiError(f"state dtype {dtype} not supported")
+        self.triple = triple
+        self.K = triple.K
+        if len(io_scaling) != self.K:
+            raise NiError(f"io_scaling has {len(io_scaling)} entries, matrix has K={self.K}")
+        self.io = [tuple(float(v) for v in t) for t in io_scaling]
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NiError("NaturalInferenceSampler runs on CUDA only; there is no CPU fallback")
+        _lib.lib()
+        self.dtype = dtype
+        self.batch = int(batch)
+        self.sample_shape = tuple(int(s) for s in sample_shape)
+        self.per_sample = int(np.prod(self.sample_shape))
+        self.numel = self.batch * self.per_sample
+        self.seed = int(seed)
+        self.eps0_mode = eps0
+        self.lp_dtype = lp_dtype
+        self.elem_offset = int(sample_offset) * self.per_sample
+        self.plan: StepPlan = build_plan(triple, keep_all_x0=keep_all_x0)
+        p = self.plan
+        # one slab: X ping-pong (2) + eps0 (1) + x0 ring + eps ring
+        n_buf = 3 + p.n_x0_slots + p.n_eps_slots
+        self._slab = torch.empty((n_buf, self.numel), dtype=dtype, device=self.device)
+        self._X = [self._slab[0], self._slab[1]]
+        self._eps0 = self._slab[2]
+        self._x0_slots = [self._slab[3 + i] for i in range(p.n_x0_slots)]
+        self._eps_slots = [self._slab[3 + p.n_x0_slots + i] for i in range(p.n_eps_slots)]
+        self._lp = [torch.empty(self.numel, dtype=lp_dtype, device=self.device) for _ in range(2)] if lp_dtype else None
+        self.sumsq = torch.zeros((self.K, self.batch), dtype=torch.float32, device=self.device) if track_sumsq else None
+        self._launches: Optional[List[List[StepLaunch]]] = None
+        self._launch_key = None
+        self._graph = None
+        self._graph_out = None
+        self.kernel_launches_per_trajectory = sum(p.launches(k, eps0 == "stored") for k in range(self.K))
+
+    # ------------------------------------------------------------------ views
+    def full_shape(self):
+        return (self.batch,) + self.sample_shape
+
+    def x0_slot(self, j: int) -> Optional[torch.Tensor]:
+        s = self.plan.x0_slot_of[j]
+        return None if s < 0 else self._x0_slots[s].view(self.full_shape())
+
+    def state_bytes(self) -> int:
+        return self._slab.numel() * self._slab.element_size()
+
+    # ------------------------------------------------------------------ launch preparation
+    def _prepare(self, x_init_ptr: int, eps0_ptr: int, fresh_ptrs: Optional[Sequence[int]], out_ptr: int, stored0: bool):
+        key = (x_init_ptr, eps0_ptr, tuple(fresh_ptrs) if fresh_ptrs is not None else None, out_ptr, stored0)
+        if self._launches is not None and key == self._launch_key:
+            return
+        p, code = self.plan, DTYPE_CODE[self.dtype]
+        launches: List[List[StepLaunch]] = []
+        for k, s in enumerate(p.steps):
+            x_in = x_init_ptr if k == 0 else self._X[k % 2].data_ptr()
+            x_next = self._X[(k + 1) % 2].data_ptr()
+            if k == self.K - 1 and out_ptr:
+                x_next = out_ptr
+            terms = [(self._x0_slots[p.x0_slot_of[j]].data_ptr(), c) for j, c in s.hist]
+            gens = []
+            for j, c in s.eps:
+                if j == 0:
+                    if stored0:
+                        terms.append((eps0_ptr, c))
+                    else:
+                        gens.append((0, c, 0))
+                elif fresh_ptrs is not None:
+                    terms.append((fresh_ptrs[j - 1], c))
+                else:
+                    terms.append((self._eps_slots[p.eps_slot_of[j]].data_ptr(), c))
+            if s.fresh is not None:
+                if fresh_ptrs is not None:
+                    if s.fresh != 0.0:
+                        terms.append((fresh_ptrs[k], s.fresh))
+                else:
+                    dst = self._eps_slots[s.fresh_slot].data_ptr() if s.keep_fresh else 0
+                    gens.append((k + 1, s.fresh, dst))
+            a, b0, b1 = self.io[k]
+            common = dict(numel=self.numel, per_sample=self.per_sample, dtype=code, seed=self.seed, elem_offset=self.elem_offset)
+            chunks = [terms[i:i + NI_MAX_TERMS] for i in range(0, max(len(terms), 1), NI_MAX_TERMS)]
+            row = []
+            for ci, chunk in enumerate(chunks):
+                last = ci == len(chunks) - 1
+                row.append(StepLaunch(
+                    **common, has_x0=ci == 0, x_in=x_in if ci == 0 else 0, a=a, b0=b0, b1=b1,
+                    x0_dst=(self._x0_slots[s.x0_slot].data_ptr() if (s.keep_x0 and ci == 0) else 0), c_x0=s.c_x0,
+                    terms=chunk, gens=gens if ci == 0 else (), accumulate=ci > 0, x_next=x_next,
+                    x_next_lp=(self._lp[(k + 1) % 2].data_ptr() if (self._lp is not None and last) else 0),
+                    lp_dtype=DTYPE_CODE[self.lp_dtype] if self.lp_dtype else NI_BF16,
+                    sumsq=(self.sumsq[k].data_ptr() if (self.sumsq is not None and last) else 0)))
+            launches.append(row)
+        self._launches, self._launch_key = launches, key
+
+    def _check_out(self, o: torch.Tensor, k: int):
+        if not o.is_cuda or not o.is_contiguous():
+            raise NiError(f"denoiser output at step {k} must be a contiguous CUDA tensor")
+        if o.dim() < 2 or o.shape[0] != self.batch or o.numel() % self.batch != 0 or o.numel() // self.batch < self.per_sample:
+            raise NiError(f"denoiser output at step {k} has shape {tuple(o.shape)}; expected [B={self.batch}, >= {self.per_sample} elements]")
+
+    def step(self, k: int, outs, stream: Optional[int] = None):
+        """Launch step k on model output(s) `outs` (after _prepare)."""
+        if isinstance(outs, torch.Tensor):
+            outs = (outs,)
+        o0 = outs[0]
+        self._check_out(o0, k)
+        row = self._launches[k]
+        d = row[0].desc
+        d.out0 = o0.data_ptr()
+        d.out_dtype = DTYPE_CODE[o0.dtype]
+        d.out_sample_stride = o0.numel() // self.batch
+        if len(outs) > 1 and outs[1] is not None:
+            self._check_out(outs[1], k)
+            if outs[1].dtype != o0.dtype or outs[1].shape != o0.shape:
+                raise NiError("both denoiser outputs must share dtype and shape")
+            d.out1 = outs[1].data_ptr()
+        else:
+            d.out1 = None
+            if self.io[k][2] != 0.0:
+                raise NiError(f"io_scaling[{k}] has b1 != 0 but the denoiser returned one tensor")
+        st = stream_ptr(self.device) if stream is None else stream
+        for L in row:
+            L.launch(st)
+
+    # ------------------------------------------------------------------ the loop
+    @torch.no_grad()
+    def sample(self, denoiser: Callable, noise: Optional[torch.Tensor] = None, fresh_noise: Optional[Sequence[torch.Tensor]] = None,
+               out: Optional[torch.Tensor] = None, record: bool = False):
+        """Run the K-step trajectory.  Returns x_K (a view of internal state unless `out` is given;
+        valid until the next call).  With record=True returns (x_K, trace) where trace[k] has clones
+        of x0_k and x_{k+1} (needs keep_all_x0=True)."""
+        if record and any(s < 0 for s in self.plan.x0_slot_of):
+            raise NiError("record=True needs a sampler built with keep_all_x0=True")
+        shape = self.full_shape()
+        with torch.cuda.device(self.device):
+            if noise is not None:
+                if noise.shape != shape or noise.dtype != self.dtype or not noise.is_cuda or not noise.is_contiguous():
+                    raise NiError(f"noise must be a contiguous CUDA {self.dtype} tensor of shape {shape}")
+                x_init = eps0 = noise
+            else:
+                tgt = self._eps0 if self.eps0_mode == "stored" else self._X[0]
+                x_init = eps0 = philox_normal(shape, seed=self.seed, tensor_id=0, elem_offset=self.elem_offset, out=tgt.view(shape))
+            fresh_ptrs = None
+            if fresh_noise is not None:
+                if len(fresh_noise) != self.K:
+                    raise NiError(f"fresh_noise needs K={self.K} tensors")
+                for t in fresh_noise:
+                    if t.shape != shape or t.dtype != self.dtype or not t.is_cuda or not t.is_contiguous():
+                        raise NiError("fresh_noise tensors must match the state shape/dtype and be contiguous CUDA tensors")
+                fresh_ptrs = [t.data_ptr() for t in fresh_noise]
+            if out is not None and (out.shape != shape or out.dtype != self.dtype or not out.is_cuda or not out.is_contiguous()):
+                raise NiError("out must match the state shape/dtype and be a contiguous CUDA tensor")
+            # caller-provided noise is always read through its pointer (it need not be the Philox tensor)
+            stored0 = self.eps0_mode == "stored" or noise is not None
+            self._prepare(x_init.data_ptr(), eps0.data_ptr(), fresh_ptrs, out.data_ptr() if out is not None else 0, stored0)
+            if self.sumsq is not None:
+                self.sumsq.zero_()
+            st = stream_ptr(self.device)
+            trace = []
+            x = x_init.view(shape)
+            for k in range(self.K):
+                x_model = x if (self._lp is None or k == 0) else self._lp[k % 2].view(shape)
+                outs = denoiser(x_model, k)
+                self.step(k, outs, st)
+                x = (out if (k == self.K - 1 and out is not None) else self._X[(k + 1) % 2]).view(shape)
+                if record:
+                    trace.append(dict(x0=self.x0_slot(k).clone(), x_next=x.clone()))
+        return (x, trace) if record else x
+
+    # ------------------------------------------------------------------ CUDA graph of the whole trajectory
+    @torch.no_grad()
+    def capture(self, denoiser: Callable, noise: Optional[torch.Tensor] = None):
+        """Capture the K steps (denoiser included) in one CUDA graph.  `noise` (if given) is a static
+        input buffer the caller refills between replays; otherwise noise is generated inside the graph
+        from the sampler seed (same tensors every replay unless `self.seed` handling is external)."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.sample(denoiser, noise=noise)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self.sample(denoiser, noise=noise)
+            self._graph, self._graph_out = g, res
+        return g
+
+    def replay(self) -> torch.Tensor:
+        if self._graph is None:
+            raise NiError("capture() first")
+        self._graph.replay()
+        return self._graph_out
+
+    # ------------------------------------------------------------------ host-buffer entry (end-to-end)
+    @torch.no_grad()
+    def sample_host(self, denoiser: Callable, noise_host: torch.Tensor, out_host: torch.Tensor, pixels: bool = False):
+        """End-to-end call with HOST buffers: pinned fp noise in, result out (fp state, or NHWC uint8
+        pixels when pixels=True, fused output stage of src/CIFAR10NaturalInference.py:308-309).
+        Copies are asynchronous on the current stream; the caller synchronises."""
+        shape = self.full_shape()
+        if noise_host.device.type != "cpu" or noise_host.shape != shape or noise_host.dtype != self.dtype:
+            raise NiError("noise_host must be a CPU tensor matching the state shape/dtype")
+        dev_noise = self._eps0.view(shape) if self.eps0_mode == "stored" else self._X[0].view(shape)
+        dev_noise.copy_(noise_host, non_blocking=True)
+        x = self.sample(denoiser, noise=dev_noise)
+        if pixels:
+            if not hasattr(self, "_pix"):
+                b, (c, h, w) = self.batch, self.sample_shape
+                self._pix = torch.empty((b, h, w, c), dtype=torch.uint8, device=self.device)
+            x = to_pixel_u8(x, out=self._pix)
+        out_host.copy_(x, non_blocking=True)
+        return out_host
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous batch shard [start, stop) of rank `rank` (samples are independent, so
+    there is no collective on the sampling path)."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

@@ -1,0 +1,423 @@
+"""CPU oracle for the Natural Inference (NI) sampling step.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``naturaldiffusion_b200/`` imports this
+module; it is imported by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` as the checker and
+the reported CPU baseline -- never as the product path.
+
+What it is: a restatement, in plain torch-on-CPU / numpy, of the arithmetic the
+reference (blairstar/NaturalDiffusion) performs on the NI hot path, keeping the
+reference's dtypes and rounding points (fp64 history for the CIFAR loop, fp32
+product / fp64 accumulate for the DiT loop, storage-dtype accumulate for the SD3
+loop).  Each function cites the reference file:line it follows.
+
+Pinning: ``tests/golden/make_golden.py`` imports the reference's *own* functions
+from /root/reference (third-party modules stubbed, see ``oracle/ref_loader.py``),
+runs them on seeded inputs and commits the outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this restatement against those vectors
+and against the 46 shipped coefficient matrices.  Parity is therefore pinned.
+"""
+from __future__ import annotations
+
+import io
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------------------
+# coefficient triples (reference: src/Utils.py:49 writer, read by position at
+# src/CIFAR10NaturalInference.py:273 and src/ValidateNaturalInference.py:319)
+# --------------------------------------------------------------------------------------
+
+
+def load_triple(path):
+    """(A, B, node) by POSITION, as ``np.load(p).values()`` does in the reference."""
+    with np.load(path) as z:
+        A, B, node = [z[k] for k in z.files]
+    return A, B, node
+
+
+def load_sd3_csv(path):
+    """28x28 weight table; first column is the index, header row the sigmas.
+
+    Follows ``pd.read_csv(path, index_col=0).to_numpy()`` (src/SD3NaturalInference.py:196)
+    without pandas so the oracle has no dependency the product does not have.
+    """
+    with open(path, "r") as f:
+        rows = [ln.strip().split(",") for ln in f if ln.strip()]
+    return np.array([[float(v) for v in r[1:]] for r in rows[1:]], dtype=np.float64)
+
+
+def sd3_sigmas(num_step=28, shift=3.0, num_train=1000):
+    """FlowMatchEulerDiscreteScheduler.set_timesteps(28) of diffusers (third party, absent
+    here; version unpinned in the reference's requirements.txt:14), as called at
+    src/SD3NaturalInference.py:188-190.  Published algorithm restated:
+      __init__ : sigma_min = shift*s/(1+(shift-1)*s) at s = 1/num_train, sigma_max = 1
+      set_timesteps(n): u = linspace(sigma_max, sigma_min, n); sigma = shift*u/(1+(shift-1)*u);
+                        append a trailing 0; stored as float32.
+    Anchored on the reference's own csv headers (sigma rounded to 2 decimals) and on the
+    csv body (W[k,j] = round(100*(sigma_j - sigma_{j+1}), 2)), see tests/test_oracle_golden.py.
+    """
+    s_min = 1.0 / num_train
+    sigma_min = shift * s_min / (1 + (shift - 1) * s_min)
+    u = np.linspace(1.0, sigma_min, num_step, dtype=np.float32).astype(np.float64)
+    sig = shift * u / (1 + (shift - 1) * u)
+    return np.append(sig, 0.0).astype(np.float32)
+
+
+def sd3_triple(W, sigmas):
+    """csv table -> (A, B, node) of the common NI form:
+    model input of step k+1 = sigma_{k+1}*noise + (1-sigma_{k+1}) * sum_j W[k,j] x0_j / sum_j W[k,j]
+    (src/SD3NaturalInference.py:207-209 with :157-168)."""
+    K = W.shape[0]
+    sig = np.asarray(sigmas, dtype=np.float64)
+    A = np.zeros((K, K))
+    B = np.zeros((K, K + 1))
+    for k in range(K):
+        row = W[k, : k + 1]
+        A[k, : k + 1] = (1.0 - sig[k + 1]) * row / row.sum()
+        B[k, 0] = sig[k + 1]
+    node = np.stack([sig, 1.0 - sig, sig], axis=1)
+    return A, B, node
+
+
+# --------------------------------------------------------------------------------------
+# DDPM / DDIM schedule tables (reference: src/ValidateNaturalInference.py:28-174, same
+# code duplicated at src/AnalyzeDDPMDDIM.py:20-123)
+# --------------------------------------------------------------------------------------
+
+
+def spaced_steps(num_timesteps: int, count: int):
+    """Single-section case of ``space_timesteps(1000, str(count))``
+    (src/ValidateNaturalInference.py:57-78): accumulate a float stride and
+    round-half-even each node."""
+    if count <= 1:
+        stride = 1.0
+    else:
+        stride = (num_timesteps - 1) / (count - 1)
+    cur, out = 0.0, []
+    for _ in range(count):
+        out.append(round(cur))
+        cur += stride
+    return sorted(set(out))
+
+
+def _alphas_bar():
+    betas = np.linspace(0.0001, 0.02, 1000, dtype=np.float64)
+    return np.cumprod(1.0 - betas)
+
+
+def skip_tables(num_step: int):
+    """Quantities of skip_ddpm_coeff / skip_ddim_coeff on the sub-sampled grid
+    (src/ValidateNaturalInference.py:98-174). Index 0 = lowest noise level."""
+    idx = spaced_steps(1000, num_step)
+    ab = _alphas_bar()[idx]
+    ab_prev = np.append(1.0, ab[:-1])
+    alphas = ab / ab_prev
+    betas = 1.0 - alphas
+    var = betas * (1.0 - ab_prev) / (1.0 - ab)
+    out = dict(
+        idx=idx,
+        alphas_bar=ab,
+        alphas=alphas,
+        log_var=np.log(np.append(1e-5, var[1:])),
+        xt2x0=np.sqrt(1.0 / ab),
+        eps2x0=np.sqrt(1.0 / ab - 1.0),
+        ddpm_x0=np.sqrt(ab_prev) * betas / (1.0 - ab),
+        ddpm_xt=np.sqrt(alphas) * (1.0 - ab_prev) / (1.0 - ab),
+    )
+    rect = np.sqrt((1.0 - ab_prev) / (1.0 - ab))
+    out["ddim_xt"] = rect
+    out["ddim_x0"] = np.sqrt(ab_prev) - rect * np.sqrt(ab)
+    return out
+
+
+def _first_order_rows(coef_xt, coef_x0, std):
+    """Unroll x_{s-1} = coef_xt[s] x_s + coef_x0[s] x0_s + std[s] eps into matrix rows
+    (closed forms of src/AnalyzeDDPMDDIM.py:126-174, :297-340 and
+    src/AnalyzeFlowMatching.py:20-59).  Sampling order runs from index K-1 down to 0."""
+    K = len(coef_xt)
+    A = np.zeros((K, K))
+    B = np.zeros((K, K + 1))
+    for start in range(K):
+        r = K - start - 1  # row = state after the step that lands on level `start`
+        eps = [np.prod(coef_xt[start:K])]
+        xz = []
+        for ii in range(start, K)[::-1]:
+            f = float(np.prod(coef_xt[start:ii]))
+            if std is not None:
+                eps.append(float(std[ii]) * f)
+            xz.append(float(coef_x0[ii]) * f)
+        B[r, : len(eps)] = eps
+        A[r, : len(xz)] = xz
+    return A, B
+
+
+def ddim_triple(num_step: int):
+    """src/AnalyzeDDPMDDIM.py:297-340 (`ddim_analyze_coeff`)."""
+    t = skip_tables(num_step)
+    K = num_step
+    node = np.zeros((K + 1, 3))
+    node[0] = [999, 0.0, 1.0]
+    for start in range(K):
+        if start == 0:
+            node[K - start] = [-1, 1.0, 0.0]
+        else:
+            node[K - start] = [t["idx"][start - 1], np.sqrt(t["alphas_bar"][start - 1]), np.sqrt(1 - t["alphas_bar"][start - 1])]
+    A, B = _first_order_rows(t["ddim_xt"], t["ddim_x0"], None)
+    return A, B, node
+
+
+def ddpm_triple(num_step: int):
+    """src/AnalyzeDDPMDDIM.py:126-174 (`ddpm_analyze_coeff`)."""
+    t = skip_tables(num_step)
+    K = num_step
+    std = np.sqrt(np.exp(t["log_var"]))
+    node = np.zeros((K + 1, 3))
+    node[0] = [999, 0.0, 1.0]
+    for start in range(K):
+        if start == 0:
+            node[K - start] = [-1, 1.0, 0.0]
+        else:
+            node[K - start] = [t["idx"][start - 1], np.sqrt(t["alphas_bar"][start - 1]), np.sqrt(1 - t["alphas_bar"][start - 1])]
+    A, B = _first_order_rows(t["ddpm_xt"], t["ddpm_x0"], std)
+    return A, B, node
+
+
+def flow_euler_triple(num_step: int):
+    """src/AnalyzeFlowMatching.py:20-59 (`flow_analyze_coeff`)."""
+    sig = np.linspace(0, 1, num_step + 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cxt = sig[:-1] / sig[1:]
+    cx0 = 1.0 - cxt
+    K = num_step
+    node = np.zeros((K + 1, 3))
+    node[0] = [1.0, 0.0, 1.0]
+    for start in range(K):
+        node[K - start] = [sig[start], 1 - sig[start], sig[start]]
+    A, B = _first_order_rows(cxt, cx0, None)
+    return A, B, node
+
+
+# --------------------------------------------------------------------------------------
+# the per-step functions, reference dtypes and rounding points kept
+# --------------------------------------------------------------------------------------
+
+
+@torch.no_grad()
+def cifar_data_fn(score_fn, xt, t, x_coeff, eps_coeff):
+    """src/CIFAR10NaturalInference.py:219-230: pred_x0 = (score*sigma^2 + xt)/alpha in fp64."""
+    vec_t = t * torch.ones(xt.shape[0])
+    score = score_fn(xt, vec_t)
+    xt64 = xt.to(torch.float64)
+    s64 = score.to(torch.float64)
+    e = torch.tensor(eps_coeff, dtype=torch.float64)
+    a = torch.tensor(x_coeff, dtype=torch.float64)
+    return (s64 * e**2 + xt64) / a
+
+
+def cifar_weighted_sum(row, seq_x0):
+    """src/CIFAR10NaturalInference.py:233-238: accumulate in the history dtype (fp64), cast fp32.
+    Zero coefficients are multiplied too."""
+    out = torch.zeros_like(seq_x0[0])
+    for ii, x0 in enumerate(seq_x0):
+        out += x0 * row[ii]
+    return out.to(torch.float32)
+
+
+def validate_weighted_sum(weights, seq_elem):
+    """src/ValidateNaturalInference.py:198-204: fp32 product, fp64 accumulator, fp32 result."""
+    out = torch.zeros_like(seq_elem[0]).to(torch.float64)
+    for ii, elem in enumerate(seq_elem):
+        out += elem * weights[ii]
+    return out.to(torch.float32)
+
+
+def sd3_weighted_sum(seq_xstarts, weights=None):
+    """src/SD3NaturalInference.py:157-168: row len(seq)-1, accumulate in the tensors' dtype,
+    divide by the python-float row sum."""
+    n = len(seq_xstarts)
+    acc_w = 0
+    acc = torch.zeros_like(seq_xstarts[0])
+    for ii, arr in enumerate(seq_xstarts):
+        w = 1 if weights is None else weights[n - 1][ii]
+        acc += arr * w
+        acc_w += w
+    return acc / acc_w
+
+
+def euler_weighted_sum(seq_xstarts, cliplen=0):
+    """src/SD3NaturalInference.py:61-69."""
+    acc = torch.zeros_like(seq_xstarts[0][1])
+    acc_w = 0
+    for w, x in seq_xstarts[-cliplen:]:
+        acc += w * x
+        acc_w += w
+    return acc, acc / acc_w
+
+
+def vp_marginal_std(t, beta_0=0.1, beta_1=20.0):
+    """deps/score_sde_pytorch/sde_lib.py:141-145, fp32 torch arithmetic on a [B] tensor."""
+    lmc = -0.25 * t**2 * (beta_1 - beta_0) - 0.5 * t * beta_0
+    return torch.sqrt(1.0 - torch.exp(2.0 * lmc))
+
+
+def make_vp_score_fn(model_fn):
+    """deps/score_sde_pytorch/models/utils.py:144-160 (continuous VP branch)."""
+
+    def score_fn(x, t):
+        h = model_fn(x, t * 999)
+        std = vp_marginal_std(t)
+        return -h / std[:, None, None, None]
+
+    return score_fn
+
+
+# --------------------------------------------------------------------------------------
+# the three loops; each returns (final, trace) with trace = list of per-step dicts
+# --------------------------------------------------------------------------------------
+
+
+@torch.no_grad()
+def cifar_ni_loop(A, B, node, score_fn, noise):
+    """src/CIFAR10NaturalInference.py:292-306."""
+    ts = node[:, 0]
+    K = ts.shape[0] - 1
+    seq_x0, trace = [], []
+    x = noise
+    for kk in range(K):
+        pred_x0 = cifar_data_fn(score_fn, x, ts[kk], node[kk, 1], node[kk, 2])
+        seq_x0.append(pred_x0)
+        next_x0 = cifar_weighted_sum(A[kk], seq_x0)
+        next_eps = B[kk, 0] * noise
+        x = next_x0 + next_eps
+        trace.append(dict(x0=pred_x0, x_next=x))
+    return x, trace
+
+
+@torch.no_grad()
+def validate_ni_loop(A, B, node, eps_model: Callable, noise, fresh_noise: Sequence[torch.Tensor], cfg_scale=4.0):
+    """src/ValidateNaturalInference.py:343-366.  ``eps_model(z, timestep:int) -> (cond, uncond)``
+    plays `forward_cfg` (:185-195) minus the fuse; ``fresh_noise[k]`` is the tensor
+    `torch.randn_like` returns at step k (:359)."""
+    K = B.shape[0]
+    t = skip_tables(K)
+    c1 = torch.from_numpy(t["xt2x0"]).to(torch.float32).flip(0)
+    c2 = torch.from_numpy(t["eps2x0"]).to(torch.float32).flip(0)
+    seq_x0, seq_eps, trace = [], [noise], []
+    z = noise.clone()
+    for kk in range(K):
+        cond, uncond = eps_model(z, int(node[kk, 0]))
+        fuse = uncond + cfg_scale * (cond - uncond)
+        pred_x0 = c1[kk] * z - c2[kk] * fuse
+        seq_x0.append(pred_x0)
+        seq_eps.append(fresh_noise[kk])
+        z = validate_weighted_sum(A[kk], seq_x0) + validate_weighted_sum(B[kk], seq_eps)
+        trace.append(dict(x0=pred_x0, x_next=z))
+    return z, trace
+
+
+@torch.no_grad()
+def ddpm_original_loop(num_step, eps_model, noise, fresh_noise, cfg_scale=4.0):
+    """src/ValidateNaturalInference.py:235-250 (ancestral sampling, the comparator).
+    fresh_noise[k] is consumed at the k-th executed step (sampling order)."""
+    t = skip_tables(num_step)
+    f32 = lambda a: torch.from_numpy(a).to(torch.float32)
+    c1, c2, cxt, cx0, lv = f32(t["xt2x0"]), f32(t["eps2x0"]), f32(t["ddpm_xt"]), f32(t["ddpm_x0"]), f32(t["log_var"])
+    z = noise.clone()
+    trace = []
+    for n, ii in enumerate(range(num_step)[::-1]):
+        cond, uncond = eps_model(z, t["idx"][ii])
+        fuse = uncond + cfg_scale * (cond - uncond)
+        x0 = c1[ii] * z - c2[ii] * fuse
+        mean = cxt[ii] * z + cx0[ii] * x0
+        z = mean + torch.exp(0.5 * lv[ii]) * fresh_noise[n]
+        trace.append(dict(x0=x0, x_next=z))
+    return z, trace
+
+
+@torch.no_grad()
+def ddim_original_loop(num_step, eps_model, noise, cfg_scale=4.0):
+    """src/ValidateNaturalInference.py:288-302."""
+    t = skip_tables(num_step)
+    f32 = lambda a: torch.from_numpy(a).to(torch.float32)
+    c1, c2, cxt, cx0 = f32(t["xt2x0"]), f32(t["eps2x0"]), f32(t["ddim_xt"]), f32(t["ddim_x0"])
+    z = noise.clone()
+    trace = []
+    for ii in range(num_step)[::-1]:
+        cond, uncond = eps_model(z, t["idx"][ii])
+        fuse = uncond + cfg_scale * (cond - uncond)
+        x0 = c1[ii] * z - c2[ii] * fuse
+        z = cxt[ii] * z + cx0[ii] * x0
+        trace.append(dict(x0=x0, x_next=z))
+    return z, trace
+
+
+@torch.no_grad()
+def sd3_ni_loop(W, sigmas, v_model: Callable, noises, cfg_scale=7):
+    """src/SD3NaturalInference.py:198-223.  ``v_model(x_in, k) -> (v_text, v_null)``.
+    Arithmetic runs in ``noises.dtype`` (the reference uses fp16); sigmas are fp32 0-d tensors."""
+    K = W.shape[0]
+    sig = torch.as_tensor(np.asarray(sigmas), dtype=torch.float32)
+    seq, trace = [], []
+    out = None
+    for kk in range(K):
+        sigma = sig[kk]
+        curr = sd3_weighted_sum(seq, W) if len(seq) != 0 else torch.zeros_like(noises)
+        x_in = sigma * noises + (1 - sigma) * curr
+        v_text, v_null = v_model(x_in, kk)
+        x0_null = x_in - sigma * v_null
+        x0_text = x_in - sigma * v_text
+        x0 = x0_null + cfg_scale * (x0_text - x0_null)
+        seq.append(x0)
+        out = sd3_weighted_sum(seq, W)
+        trace.append(dict(x_in=x_in, x0=x0, out=out))
+    return out, trace
+
+
+@torch.no_grad()
+def sd3_euler_original_loop(sigmas, v_model, noises, cfg_scale=7):
+    """src/SD3NaturalInference.py:104-127 with is_vanilla_update=True (the Euler comparator)."""
+    sig = torch.as_tensor(np.asarray(sigmas), dtype=torch.float32)
+    x = noises.clone()
+    for i in range(len(sig) - 1):
+        v_text, v_null = v_model(x, i)
+        fuse = v_null + cfg_scale * (v_text - v_null)
+        x = x + (sig[i + 1] - sig[i]) * fuse
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# common-form loop in fp64: the yardstick for "one fused step"
+# --------------------------------------------------------------------------------------
+
+
+def ni_step_f64(a, b, x_in, outs, A_row, x0_hist, B_row, eps_hist):
+    """x0 = a*x + sum_m b[m]*out[m];  x_next = sum_j A_row[j]*x0_j + sum_j B_row[j]*eps_j, all in fp64."""
+    x0 = a * x_in.to(torch.float64)
+    for bm, o in zip(b, outs):
+        x0 = x0 + bm * o.to(torch.float64)
+    hist = list(x0_hist) + [x0]
+    nxt = torch.zeros_like(x0)
+    for j, h in enumerate(hist):
+        if A_row[j] != 0:
+            nxt += A_row[j] * h.to(torch.float64)
+    for j, e in enumerate(eps_hist):
+        if j < len(B_row) and B_row[j] != 0:
+            nxt += B_row[j] * e.to(torch.float64)
+    return x0, nxt
+
+
+def to_pixel_u8(x):
+    """Output stage: inverse scaler (x+1)/2 (deps/score_sde_pytorch/datasets.py:32-38 for centered
+    data) then src/CIFAR10NaturalInference.py:212-216: NCHW->NHWC, clip(x*255,0,255), truncating uint8."""
+    y = (x + 1.0) / 2.0
+    y = y.permute(0, 2, 3, 1).contiguous().numpy()
+    return np.clip(y * 255, 0, 255).astype(np.uint8)
+
+
+def npz_bytes(**arrays):
+    buf = io.BytesIO()
+    np.savez(buf, **arrays)
+    return buf.getvalue()
