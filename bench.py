@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- Natural Inference update throughput on B200 (contract: see the task's bench section).
+
+Workload (BASELINE.json configs[1], "C2"): CIFAR-10 32x32 Natural Inference with the reference's
+step_10_weight_42 coefficient matrix, batch 4096 per GPU, fp32 state.  One bench "step" = one full
+K=10-step NI trajectory over one batch: 10 fused `ni_step` launches, 65 tensor-sized HBM transfers
+(3.27 GB algorithmic).  The denoiser is the *null denoiser* of SURVEY 8d (a pre-generated N(0,1)
+model-output tensor re-read from HBM every step), so the timed region contains only our kernels:
+the denoiser forward stays torch and is not what this repo accelerates.
+
+  value     samples/s, inputs resident in HBM, whole job over all ranks (weak scaling: 4096 samples/GPU)
+  e2e       same metric through NaturalInferenceSampler.sample_host(): pinned host noise -> H2D -> 10 steps
+            -> fused uint8 pixel stage -> D2H, copies inside the timed region
+  roofline  algorithmic bytes per ni_step launch / mean launch duration (CUDA events over the timed region)
+  cpu_baseline / --impl reference: the oracle's torch-CPU restatement of the reference loop
+            (src/CIFAR10NaturalInference.py:219-238,294-304) on this box's host cores -- the reference is
+            pure Python/torch, there is nothing to compile into oracle/_ref.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "reference_weights")
+CONFIGS = {
+    # name: (matrix file, per-GPU batch, sample shape, model outputs)
+    "c2": ("step_10_weight_42.npz", 4096, (3, 32, 32), 1),
+    "c3": ("step_15_weight_173.npz", 16384, (3, 32, 32), 1),
+}
+METRIC = "NI-update samples/sec (HBM GB/s and % peak in `roofline`)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--eps0", default="stored", choices=["stored", "regen"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop, null denoiser
+# ----------------------------------------------------------------------------------------------
+def cpu_trajectory(A, B, node, noise, h):
+    """Reference arithmetic (oracle restatement) for one batch; `h` plays the raw net output."""
+    import torch
+    from oracle import ni_oracle as O
+    score_fn = O.make_vp_score_fn(lambda x, labels: h)
+    x, _ = O.cifar_ni_loop(A, B, node, score_fn, noise)
+    return x
+
+
+def time_cpu(cfg, batch, reps, warm):
+    import torch
+    from oracle import ni_oracle as O
+    fname, _, shape, _ = CONFIGS[cfg]
+    A, B, node = O.load_triple(os.path.join(WEIGHTS, fname))
+    g = torch.Generator().manual_seed(888)
+    noise = torch.randn((batch,) + shape, generator=g)
+    h = torch.randn((batch,) + shape, generator=g)
+    for _ in range(warm):
+        cpu_trajectory(A, B, node, noise, h)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_trajectory(A, B, node, noise, h)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank):
+    """`--impl reference`: rank 0 alone times the reference's CPU path; other ranks exit."""
+    if rank != 0:
+        return
+    import torch
+    cores = torch.get_num_threads()
+    fname, full_batch, shape, m = CONFIGS[args.config]
+    # bounded sample: size the batch so (steps+warmup) trajectories take about two minutes
+    probe = time_cpu(args.config, 128, 1, 1)[0]
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    batch = int(max(64, min(full_batch, 128 * budget / probe)))
+    batch -= batch % 64
+    ts = time_cpu(args.config, batch, args.steps, args.warmup)
+    total = sum(ts)
+    val = batch * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 history / f32 state (reference dtypes)", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {fname} update-only, null denoiser, sample of {batch} of {full_batch} samples per step",
+                   "shape": [batch] + list(shape)},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{batch}-sample batches x {args.steps} trajectories; torch {torch.__version__} CPU; {cpu_model()}"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [v.strip() for v in ln.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(cfg, eps0):
+    """DRAM bytes per ni_step launch from the committed ncu --set full capture, if one matches this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(f"{cfg}:{eps0}")
+    except Exception:
+        return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import naturaldiffusion_b200 as ni
+    from naturaldiffusion_b200.sampler import NaturalInferenceSampler
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fname, batch, shape, m = CONFIGS[args.config]
+    batch = args.batch or batch
+    triple = ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, fname))
+    K = triple.K
+    sampler = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), batch, shape, device=dev, seed=888,
+                                      eps0=args.eps0, sample_offset=rank * batch)
+    from naturaldiffusion_b200.ops import philox_normal
+    h = philox_normal((batch,) + shape, seed=888, tensor_id=1000, elem_offset=sampler.elem_offset, device=dev)  # null denoiser output
+    den = lambda x, k: h
+    numel = sampler.numel
+    stored0 = args.eps0 == "stored"
+    units = sampler.plan.total_units(m, eps0_stored=stored0)
+    bytes_per_traj = units * numel * 4
+    launches_per_traj = sampler.kernel_launches_per_trajectory
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    noise = philox_normal((batch,) + shape, seed=888, tensor_id=0, elem_offset=sampler.elem_offset, device=dev)
+    c0 = ni.launch_count()
+    sampler.sample(den, noise=noise)
+    torch.cuda.synchronize()
+    counted = ni.launch_count() - c0
+    assert counted == launches_per_traj, (counted, launches_per_traj)
+    if args.no_graph:
+        run = lambda: sampler.sample(den, noise=noise)
+    else:
+        sampler.capture(den, noise=noise)
+        run = sampler.replay
+    for _ in range(max(3, args.warmup)):
+        run()
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        run()
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * batch * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    achieved = bytes_per_traj / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU == per launch (only ni_step kernels run)
+    peak, peak_src = measured_peak()
+
+    # ---- end-to-end arm: host buffers through the public sampler API
+    e2e = None
+    if not args.no_e2e:
+        noise_h = torch.empty((batch,) + shape, dtype=torch.float32).pin_memory()
+        noise_h.copy_(noise)
+        out_h = torch.empty((batch, shape[1], shape[2], shape[0]), dtype=torch.uint8).pin_memory()
+        e2e_sampler = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), batch, shape, device=dev, seed=888,
+                                              sample_offset=rank * batch)
+        for _ in range(3):
+            e2e_sampler.sample_host(den, noise_h, out_h, pixels=True)
+        barrier()
+        n_e2e = max(10, args.steps // 4)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n_e2e):
+            e2e_sampler.sample_host(den, noise_h, out_h, pixels=True)
+        s1.record()
+        barrier()
+        ems = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = t.item()
+        e2e = {"value": world * batch * n_e2e / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": noise_h.numel() * 4,
+               "d2h_bytes_per_step": out_h.numel(), "steps": n_e2e, "ms_per_step": ems / n_e2e,
+               "api": "NaturalInferenceSampler.sample_host(pixels=True): pinned fp32 noise in, NHWC uint8 out"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cb = 1024
+        ts = time_cpu(args.config, cb, 3, 1)
+        cpu = {"value": cb / min(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{cb}-sample batch of the same workload, best of 3 trajectories after 1 warm-up ({sum(ts):.1f} s CPU work); "
+                         f"torch {torch.__version__} CPU, {cpu_model()}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.config}: CIFAR-10 32x32 NI update, {fname}, batch {batch}/GPU, K={K} fused steps per trajectory, "
+                               f"null denoiser (pre-generated N(0,1) model output re-read from HBM each step)",
+                   "shape": [batch] + list(shape), "eps0": args.eps0, "cuda_graph": not args.no_graph,
+                   "l2": f"inputs larger than L2: per-trajectory working set {sampler.state_bytes() / 1e6 + numel * 4 * 2 / 1e6:.0f} MB vs 126 MB L2",
+                   "state_bytes": sampler.state_bytes()},
+        "clocks": clk,
+        "e2e": e2e,
+        "gpu_launches": launches_per_traj * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.config, args.eps0), "peak_source": peak_src,
+                     "kernel": "ni_step_kernel<float,float,4,32>", "algorithmic_bytes_per_launch": bytes_per_traj / launches_per_traj,
+                     "tensor_transfers_per_trajectory": units, "us_per_launch": 1e3 * ms_per_step / launches_per_traj,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

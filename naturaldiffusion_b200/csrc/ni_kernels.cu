@@ -669,6 +669,7 @@ extern "C" {
 int ni_weighted_sum(const void *const *src, const double *coeffs, int n_terms, void *dst, int64_t numel, int src_dtype, int dst_dtype, double scale, void *stream)
 {
     if (n_terms < 0 || n_terms > NI_MAX_TERMS) return fail(NI_ERR_TOO_MANY, "ni_weighted_sum: n_terms=%d exceeds NI_MAX_TERMS=%d", n_terms, NI_MAX_TERMS);
+    if (numel == 0) return NI_OK;
     if (numel < 0 || dst == nullptr || (n_terms > 0 && (src == nullptr || coeffs == nullptr))) return fail(NI_ERR_INVALID, "ni_weighted_sum: bad arguments");
     for (int i = 0; i < n_terms; ++i) {
         if (src[i] == nullptr) return fail(NI_ERR_INVALID, "ni_weighted_sum: src[%d] is NULL", i);
@@ -695,6 +696,7 @@ int ni_weighted_sum(const void *const *src, const double *coeffs, int n_terms, v
 
 int ni_philox_normal(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, void *stream)
 {
+    if (numel == 0) return NI_OK;
     if (dst == nullptr || numel < 0) return fail(NI_ERR_INVALID, "ni_philox_normal: bad arguments");
     const int ds = dtype_size(dst_dtype);
     if (!(dst_dtype == NI_F32 || dst_dtype == NI_F16 || dst_dtype == NI_BF16)) return fail(NI_ERR_DTYPE, "ni_philox_normal: dtype %d not supported", dst_dtype);

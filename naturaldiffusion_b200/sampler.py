@@ -140,8 +140,8 @@ class NaturalInferenceSampler:
         self._launches, self._launch_key = launches, key
 
     def _check_out(self, o: torch.Tensor, k: int):
-        if not o.is_cuda or not o.is_contiguous():
-            raise NiError(f"denoiser output at step {k} must be a contiguous CUDA tensor")
+        if not o.is_cuda:
+            raise NiError(f"denoiser output at step {k} must be a CUDA tensor")
         if o.dim() < 2 or o.shape[0] != self.batch or o.numel() % self.batch != 0 or o.numel() // self.batch < self.per_sample:
             raise NiError(f"denoiser output at step {k} has shape {tuple(o.shape)}; expected [B={self.batch}, >= {self.per_sample} elements]")
 
@@ -149,6 +149,9 @@ class NaturalInferenceSampler:
         """Launch step k on model output(s) `outs` (after _prepare)."""
         if isinstance(outs, torch.Tensor):
             outs = (outs,)
+        # a non-contiguous output (channels_last nets, einsum views) is compacted by torch first: the kernel
+        # addresses [B, C', H, W] row-major
+        outs = tuple(o if (o is None or o.is_contiguous()) else o.contiguous() for o in outs)
         o0 = outs[0]
         self._check_out(o0, k)
         row = self._launches[k]

@@ -1,0 +1,189 @@
+"""CPU: host-side logic (matrix formats, launch plan, generators, sharding) and the C-ABI surface.
+No compute entry point is exercised here (there is no GPU and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import naturaldiffusion_b200 as ni
+from naturaldiffusion_b200 import _lib, generators
+from naturaldiffusion_b200.coeffs import (CoeffTriple, build_plan, ddim_x0_coeffs, flow_match_sigmas, io_score_vp,
+                                           load_weight_csv, spaced_timesteps)
+from naturaldiffusion_b200.sampler import shard_range
+from oracle import ni_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C ABI surface
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from naturaldiffusion_b200 import build
+    build.build()
+    L = ni.lib()
+    header = open(os.path.join(ROOT, "include", "ni_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:const\s+)?[A-Za-z_0-9]+\s*\*?\s*(ni_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.ni_version() == _lib.NI_ABI_VERSION
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof/offsetof of NiStepDesc as gcc sees the header == the ctypes mirror"""
+    fields = [f[0] for f in _lib.NiStepDesc._fields_]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "ni_b200.h"\nint main(){printf("%zu", sizeof(NiStepDesc));' + \
+          "".join(f'printf(" %zu", offsetof(NiStepDesc, {f}));' for f in fields) + "return 0;}\n"
+    c = tmp_path / "layout.c"
+    c.write_text(src)
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals[0] == C.sizeof(_lib.NiStepDesc)
+    assert vals[1:] == [getattr(_lib.NiStepDesc, f).offset for f in fields]
+
+
+def test_argument_validation_needs_no_gpu():
+    L = ni.lib()
+    assert L.ni_step(None, None) == -1 and b"NULL" in L.ni_last_error()
+    d = _lib.NiStepDesc()
+    d.numel, d.per_sample = 10, 3
+    assert L.ni_step(C.byref(d), None) == -1 and b"multiple" in L.ni_last_error()
+    d.numel, d.per_sample, d.n_terms = 12, 3, 10_000
+    assert L.ni_step(C.byref(d), None) == -3
+    assert L.ni_weighted_sum(None, None, 513, None, 0, 0, 0, 1.0, None) == -3
+    assert L.ni_philox_normal(None, 4, 0, 0, 0, 0, None) == -1
+    assert L.ni_weighted_sum(None, None, 0, None, 0, 0, 0, 1.0, None) == 0  # empty input: nothing to do
+
+
+def test_missing_library_is_loud(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libni_b200.so")
+    with pytest.raises(ni.NiError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "naturaldiffusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+# ------------------------------------------------------------------ matrices / plan
+def test_liveness_matches_survey(weights_dir):
+    want = {"step_5_weight_00": 2, "step_10_weight_42": 4, "step_15_weight_173": 5}
+    for name, slots in want.items():
+        p = build_plan(CoeffTriple.from_npz(os.path.join(weights_dir, name + ".npz")))
+        assert p.n_x0_slots == slots and p.n_eps_slots == 0 and p.eps0_last_use == p.K - 1
+    sig = flow_match_sigmas(28)
+    assert build_plan(CoeffTriple.from_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight_sharp.csv"), sig)).n_x0_slots == 14
+    assert build_plan(CoeffTriple.from_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight.csv"), sig)).n_x0_slots == 27
+
+
+def test_plan_never_reads_a_recycled_slot(weights_dir):
+    """simulate the ring: every (row, column) read must find that column still resident in its slot"""
+    triples = [CoeffTriple.from_npz(os.path.join(weights_dir, n + ".npz")) for n in ("step_10_weight_42", "step_15_weight_173")]
+    triples += [generators.ddpm_triple(24), CoeffTriple.from_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight_sharp.csv"))]
+    for t in triples:
+        p = build_plan(t)
+        x0_res, eps_res = {}, {}
+        for k, s in enumerate(p.steps):
+            for j, _ in s.hist:
+                assert x0_res.get(p.x0_slot_of[j]) == j, (t.name, k, j)
+            for j, _ in s.eps:
+                if j > 0:
+                    assert eps_res.get(p.eps_slot_of[j]) == j
+            if s.keep_x0:
+                x0_res[s.x0_slot] = k
+            if s.keep_fresh:
+                eps_res[s.fresh_slot] = k + 1
+        # rebuilt row == matrix row
+        for k, s in enumerate(p.steps):
+            row = np.zeros(t.K)
+            for j, c in s.hist:
+                row[j] = c
+            row[k] = s.c_x0
+            assert np.array_equal(row, np.where(t.A[k] != 0, t.A[k], 0.0))
+
+
+def test_algorithmic_units_formula(weights_dir):
+    """bytes(k) = s*N*[m + 1 + write_x0 + (nnzA-1) + nnzB_stored + w_eps + 1]"""
+    t = CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz"))
+    p = build_plan(t)
+    nnz = (t.A != 0).sum(1)
+    for k in range(10):
+        keep = 1 if p.steps[k].keep_x0 else 0
+        assert p.units(k, 1) == 1 + 1 + keep + (nnz[k] - 1) + 1 + 0 + 1
+        assert p.units(k, 1, eps0_stored=False) == p.units(k, 1) - 1
+    assert p.total_units(1) == 65  # SURVEY's 67 minus the two x0 writes no later row reads (columns 0 and 9)
+    # dense stochastic rows (C4, ddpm_250), counted independently from the matrix: the last DDPM row has
+    # coeff_xt = 0, so it reads no history and x0_248 / eps_249 / x0_249 / eps_250 are never kept
+    t = generators.ddpm_triple(250)
+    d = build_plan(t)
+    nzA, nzB = t.A != 0, t.B != 0
+    want = 0
+    for k in range(250):
+        keep_x0 = nzA[k + 1:, k].any()
+        keep_eps = nzB[k + 1:, k + 1].any()
+        want += 2 + 1 + int(keep_x0) + (nzA[k, :k].sum()) + nzB[k, :k + 1].sum() + int(keep_eps) + 1
+    assert d.total_units(2) == want == 63497
+
+
+def test_npz_roundtrip_and_shapes(tmp_path, weights_dir):
+    t = CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz"))
+    assert t.B.shape == (10, 11)  # K x K file normalised to K x (K+1)
+    t.save_npz(tmp_path / "x.npz")
+    A, B, node = O.load_triple(tmp_path / "x.npz")  # by position, like the reference
+    assert np.array_equal(A, t.A) and np.array_equal(B, t.B) and np.array_equal(node, t.node)
+    with pytest.raises(ValueError):
+        CoeffTriple(np.triu(np.ones((3, 3))), np.zeros((3, 4)), np.zeros((4, 3)))
+    assert np.array_equal(load_weight_csv(os.path.join(weights_dir, "sd3_step_28_weight.csv")),
+                          O.load_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight.csv")))
+    assert np.array_equal(flow_match_sigmas(28), O.sd3_sigmas(28))
+
+
+def test_generators_match_reference_matrices(golden_dir):
+    m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
+    for fam, fn in (("ddim", generators.ddim_triple), ("ddpm", generators.ddpm_triple)):
+        for K in (18, 24, 100):
+            t = fn(K)
+            key = f"{fam}/{fam}_{K:03d}"
+            assert np.abs(t.A - m[key + "/A"]).max() < 1e-14 and np.abs(t.B - m[key + "/B"]).max() < 1e-14
+            assert np.array_equal(t.node, m[key + "/node"])
+            assert generators.markov_ratio(t) is not None
+    for K in (18, 24):
+        t = generators.flow_euler_triple(K)
+        key = f"flow_euler/flow_euler_simpy_{K:03d}"
+        # the reference grid is ascending sigma with the matrix in sampling order
+        assert np.abs(t.A - m[key + "/A"]).max() < 1e-14 and np.abs(t.B - m[key + "/B"]).max() < 1e-14
+    for K in (10, 250):  # the two matrices BASELINE's configs need
+        for fn, ofn in ((generators.ddim_triple, O.ddim_triple), (generators.ddpm_triple, O.ddpm_triple)):
+            t, (A, B, node) = fn(K), ofn(K)
+            assert np.abs(t.A - A).max() < 1e-14 and np.abs(t.B - B).max() < 1e-14 and np.array_equal(t.node, node)
+    m42 = CoeffTriple(*[m["dpmsolverpp/dpmsolverpp2s_024/" + n] for n in ("A", "B", "node")])
+    assert generators.markov_ratio(m42) is None  # higher-order solvers are not Markov in the rows
+
+
+def test_schedule_helpers():
+    assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
+    assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
+    c1, c2, idx = ddim_x0_coeffs(10)
+    assert abs(c1[0] - 157.41046) < 1e-4 and abs(c2[-1] - 0.01) < 1e-4 and idx[0] == 999
+    t = O.skip_tables(24)
+    assert np.allclose(c1 if len(c1) == 24 else ddim_x0_coeffs(24)[0], t["xt2x0"][::-1])
+    io = io_score_vp(np.array([[1.0, 0.0066, 1.0], [0.5, 0.5, 0.8]]))
+    assert abs(io[0][0] - 1 / 0.0066) < 1e-9 and io[0][1] < 0 and io[0][2] == 0.0
+
+
+def test_shard_range_partitions():
+    for total, world in ((4096, 8), (50000, 8), (7, 3), (5, 8)):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
