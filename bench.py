@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--eps0", default="stored", choices=["stored", "regen"])
+    ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct-load kernel, 2 TMA-staged kernel")
+    ap.add_argument("--opt", action="append", default=[], help="ni_set_option name=value (tuning)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -198,6 +200,11 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from naturaldiffusion_b200 import _lib as nilib
+    nilib.set_option("variant", args.variant)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        nilib.set_option(name, int(val))
     fname, batch, shape, m = CONFIGS[args.config]
     batch = args.batch or batch
     triple = ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, fname))
@@ -299,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": f"{args.config}: CIFAR-10 32x32 NI update, {fname}, batch {batch}/GPU, K={K} fused steps per trajectory, "
                                f"null denoiser (pre-generated N(0,1) model output re-read from HBM each step)",
-                   "shape": [batch] + list(shape), "eps0": args.eps0, "cuda_graph": not args.no_graph,
+                   "shape": [batch] + list(shape), "eps0": args.eps0, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
                    "l2": f"inputs larger than L2: per-trajectory working set {sampler.state_bytes() / 1e6 + numel * 4 * 2 / 1e6:.0f} MB vs 126 MB L2",
                    "state_bytes": sampler.state_bytes()},
         "clocks": clk,

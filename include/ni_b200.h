@@ -99,6 +99,10 @@ const char *ni_last_error(void);
 /* kernels launched by this library in this process so far (bench.py's `gpu_launches`) */
 int64_t ni_launch_count(void);
 
+/* Tuning knobs, process-wide: "variant" 0 auto | 1 direct-load kernel | 2 TMA-staged kernel when eligible;
+ * "tma_max_stages" 2..8; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4.  Results do not depend on them. */
+int ni_set_option(const char *name, int value);
+
 int ni_step(const NiStepDesc *desc_host, void *stream);
 
 /* dst = scale * sum_t coeffs[t] * src[t].  The three reference `weighted_sum`s and

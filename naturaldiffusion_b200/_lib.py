@@ -74,6 +74,8 @@ def lib():
     L.ni_version.restype = C.c_int
     L.ni_last_error.restype = C.c_char_p
     L.ni_launch_count.restype = C.c_int64
+    L.ni_set_option.argtypes = [C.c_char_p, C.c_int]
+    L.ni_set_option.restype = C.c_int
     L.ni_step.argtypes = [C.POINTER(NiStepDesc), C.c_void_p]
     L.ni_step.restype = C.c_int
     L.ni_weighted_sum.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_int64,
@@ -90,7 +92,7 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_step", "ni_weighted_sum",
+EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_set_option", "ni_step", "ni_weighted_sum",
                     "ni_philox_normal", "ni_to_pixel_u8")
 
 
@@ -98,6 +100,10 @@ def check(rc: int, what: str = "libni_b200"):
     if rc != 0:
         msg = lib().ni_last_error().decode("utf-8", "replace")
         raise NiError(f"{what} failed (rc={rc}): {msg}")
+
+
+def set_option(name: str, value: int):
+    check(lib().ni_set_option(name.encode(), int(value)), "ni_set_option")
 
 
 def launch_count() -> int:

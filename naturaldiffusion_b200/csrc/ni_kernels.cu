@@ -29,14 +29,28 @@
 #ifndef NI_STORE_POLICY
 #define NI_STORE_POLICY 0 /* 0 plain st.global, 1 st.global.cs */
 #endif
+// Geometry of the direct-load kernels, chosen by the sweep in profiles/r01_sweep.txt: 128-thread CTAs, registers
+// capped at 48 (10 CTAs = 40 warps per SM) and up to 8 independent 128-bit loads per thread.  Full occupancy
+// (<= 32 registers) and 72-register / 24-warp builds were both ~8% slower.
 #ifndef NI_BLOCK
-#define NI_BLOCK 256
+#define NI_BLOCK 128
+#endif
+#ifndef NI_TERM_BATCH_MAX
+#define NI_TERM_BATCH_MAX 8 /* independent 128-bit term loads issued back to back per thread */
+#endif
+#ifndef NI_MIN_BLOCKS
+#define NI_MIN_BLOCKS 10 /* __launch_bounds__ second argument for the direct-load step kernel */
 #endif
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+// tuning knobs (ni_set_option): which step kernel, and the TMA kernel's geometry
+std::atomic<int> g_variant{0};       // 0 auto, 1 always the LDG kernel, 2 the TMA kernel whenever eligible
+std::atomic<int> g_tma_max_stages{8};
+std::atomic<int> g_tma_smem_kb{200};
+std::atomic<int> g_tma_ctas_per_sm{1};
 
 int fail(int code, const char *fmt, ...)
 {
@@ -278,14 +292,98 @@ struct StepArgs {
     int has_x0, out_strided, accumulate, lp_dtype;
 };
 
+// acc += c * (VEC elements of T)
+template <typename T, int VEC> __device__ __forceinline__ void fma_term(float (&acc)[VEC], const Raw<T, VEC> &r, float c)
+{
+    float f[VEC];
+    unpack<T, VEC>(r, f);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, f[i], acc[i]);
+}
+
+// Everything after the stored terms are summed (shared by the LDG and the TMA kernels so both produce the same bits):
+// generated noise, x0 conversion + ring store, x_{k+1} store(s), per-sample sum of squares.
+template <typename T, typename TO, int VEC>
+__device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int64_t sample, float (&acc)[VEC], const Raw<TO, VEC> &ro0,
+                                              const Raw<TO, VEC> &ro1, const Raw<T, VEC> &rx, bool has_x0, bool has_x, bool has_o1)
+{
+    // generated noise (pure ALU; overlaps loads still in flight)
+    for (int g = 0; g < s.n_gen; ++g) {
+        float z[VEC];
+        normal_vec<VEC>(s.elem_offset + (uint64_t)e, s.gen_tid[g], s.k0, s.k1, z);
+        if (s.gen_dst[g] != nullptr) {
+            store_raw<T, VEC>(static_cast<T *>(s.gen_dst[g]) + e, pack<T, VEC>(z));
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) z[i] = round_to<T>(z[i]);
+        }
+        const float c = s.gen_c[g];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, z[i], acc[i]);
+    }
+
+    // x0 = a*x + b0*out0 + b1*out1, kept in the ring, enters the sum with A[k,k]
+    if (has_x0) {
+        float x0[VEC], f[VEC];
+        unpack<TO, VEC>(ro0, f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x0[i] = s.b0 * f[i];
+        if (has_o1) {
+            unpack<TO, VEC>(ro1, f);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x0[i] = fmaf(s.b1, f[i], x0[i]);
+        }
+        if (has_x) {
+            unpack<T, VEC>(rx, f);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x0[i] = fmaf(s.a, f[i], x0[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) x0[i] = round_to<T>(x0[i]);
+        if (s.x0_dst != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x0_dst) + e, pack<T, VEC>(x0));
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s.c_x0, x0[i], acc[i]);
+    }
+
+    // x_{k+1}
+    store_raw<T, VEC>(static_cast<T *>(s.x_next) + e, pack<T, VEC>(acc));
+    if (s.x_next_lp != nullptr) {
+        if (s.lp_dtype == NI_BF16) store_raw<__nv_bfloat16, VEC>(static_cast<__nv_bfloat16 *>(s.x_next_lp) + e, pack<__nv_bfloat16, VEC>(acc));
+        else store_raw<__half, VEC>(static_cast<__half *>(s.x_next_lp) + e, pack<__half, VEC>(acc));
+    }
+
+    // per-sample sum of squares: warp shuffle, one atomic per warp (per lane only where a warp straddles samples)
+    if (s.sumsq != nullptr) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float r = round_to<T>(acc[i]);
+            ss = fmaf(r, r, ss);
+        }
+        const unsigned mask = __activemask();
+        bool fast = mask == 0xffffffffu;
+        if (fast) {
+            const long long s0 = __shfl_sync(0xffffffffu, (long long)sample, 0);
+            fast = __all_sync(0xffffffffu, (long long)sample == s0);
+        }
+        if (fast) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(s.sumsq + sample, ss);
+        } else {
+            atomicAdd(s.sumsq + sample, ss);
+        }
+    }
+}
+
+// ---- variant 1: direct 128-bit global loads, one vector per thread ---------------------------------
 template <typename T, typename TO, int VEC, int CAP>
-__global__ void __launch_bounds__(NI_BLOCK) ni_step_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<CAP> tab)
+__global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
     if (v >= s.nvec) return;
     const int64_t e = v * VEC; // first element of this thread
 
-    // 1. issue the x0-stage loads (consumed after the term loop)
+    // issue the x0-stage loads (consumed after the term loop)
     Raw<T, VEC> rx;
     Raw<TO, VEC> ro0, ro1;
     const bool has_x0 = s.has_x0 != 0;
@@ -309,92 +407,163 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_step_kernel(const __grid_constant
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
     }
 
-    // 2. stored terms: batches of independent 128-bit loads, then the FMAs
+    // stored terms: batches of independent 128-bit loads, then the FMAs
     const int n = s.n_terms;
     int t = 0;
-#define NI_TERM_BATCH(NB)                                                                      \
-    for (; t + NB <= n; t += NB) {                                                             \
-        Raw<T, VEC> rr[NB];                                                                    \
-        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC>(static_cast<const T *>(tab.ptr[t + j]) + e); \
-        _Pragma("unroll") for (int j = 0; j < NB; ++j) {                                       \
-            float f[VEC];                                                                      \
-            unpack<T, VEC>(rr[j], f);                                                          \
-            const float c = tab.c[t + j];                                                      \
-            _Pragma("unroll") for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, f[i], acc[i]);    \
-        }                                                                                      \
+#define NI_TERM_BATCH(NB)                                                                                                     \
+    for (; t + NB <= n; t += NB) {                                                                                            \
+        Raw<T, VEC> rr[NB];                                                                                                   \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC>(static_cast<const T *>(tab.ptr[t + j]) + e);  \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) fma_term<T, VEC>(acc, rr[j], tab.c[t + j]);                            \
     }
+#if NI_TERM_BATCH_MAX >= 8
     NI_TERM_BATCH(8)
+#endif
+#if NI_TERM_BATCH_MAX >= 4
     NI_TERM_BATCH(4)
+#endif
+#if NI_TERM_BATCH_MAX >= 2
     NI_TERM_BATCH(2)
+#endif
     NI_TERM_BATCH(1)
 #undef NI_TERM_BATCH
 
-    // 3. generated noise (pure ALU; overlaps the loads still in flight)
-    for (int g = 0; g < s.n_gen; ++g) {
-        float z[VEC];
-        normal_vec<VEC>(s.elem_offset + (uint64_t)e, s.gen_tid[g], s.k0, s.k1, z);
-        if (s.gen_dst[g] != nullptr) {
-            store_raw<T, VEC>(static_cast<T *>(s.gen_dst[g]) + e, pack<T, VEC>(z));
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) z[i] = round_to<T>(z[i]);
-        }
-        const float c = s.gen_c[g];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, z[i], acc[i]);
-    }
+    step_epilogue<T, TO, VEC>(s, e, sample, acc, ro0, ro1, rx, has_x0, has_x, has_o1);
+}
 
-    // 4. x0 = a*x + b0*out0 + b1*out1, kept in the ring, enters the sum with A[k,k]
-    if (has_x0) {
-        float x0[VEC], f[VEC];
-        unpack<TO, VEC>(ro0, f);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) x0[i] = s.b0 * f[i];
-        if (has_o1) {
-            unpack<TO, VEC>(ro1, f);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) x0[i] = fmaf(s.b1, f[i], x0[i]);
-        }
-        if (has_x) {
-            unpack<T, VEC>(rx, f);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) x0[i] = fmaf(s.a, f[i], x0[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) x0[i] = round_to<T>(x0[i]);
-        if (s.x0_dst != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x0_dst) + e, pack<T, VEC>(x0));
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s.c_x0, x0[i], acc[i]);
-    }
+// ---- variant 2: TMA bulk copies into a shared-memory ring, warp-specialised -------------------------
+// One persistent CTA per SM: a producer warp streams [source][tile] slabs global->shared with
+// cp.async.bulk (one lane per source tensor, completion on an mbarrier), 256 consumer threads read their
+// 16 B of every source from shared memory, run the same epilogue, and store straight to global.
+// 4 KB per source per stage; STAGES x n_src x 4 KB (<= ~200 KB) of loads are in flight per SM regardless
+// of register pressure.  Source order in a stage: out0, [out1], [x_in], term 0..n-1.
+constexpr int TMA_CONSUMERS = 256;
+constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
+constexpr int TMA_TILE_BYTES = TMA_CONSUMERS * 16;
+constexpr int TMA_MAX_STAGES = 8;
+constexpr int TMA_MAX_SRC = 24;
+constexpr int TMA_BAR_BYTES = 128;
 
-    // 5. x_{k+1}
-    store_raw<T, VEC>(static_cast<T *>(s.x_next) + e, pack<T, VEC>(acc));
-    if (s.x_next_lp != nullptr) {
-        if (s.lp_dtype == NI_BF16) store_raw<__nv_bfloat16, VEC>(static_cast<__nv_bfloat16 *>(s.x_next_lp) + e, pack<__nv_bfloat16, VEC>(acc));
-        else store_raw<__half, VEC>(static_cast<__half *>(s.x_next_lp) + e, pack<__half, VEC>(acc));
-    }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred P1;\nNI_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra NI_DONE;\nbra NI_WAIT;\nNI_DONE:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-    // 6. per-sample sum of squares: warp shuffle, one atomic per warp (per lane only where a warp straddles samples)
-    if (s.sumsq != nullptr) {
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float r = round_to<T>(acc[i]);
-            ss = fmaf(r, r, ss);
+template <typename T>
+__global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<32> tab, int n_src, int stages, int64_t ntiles)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int TILE_ELEMS = TMA_TILE_BYTES / (int)sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + TMA_MAX_STAGES;
+    unsigned char *tiles = smem + TMA_BAR_BYTES;
+    const int tid = threadIdx.x;
+    const int64_t numel = s.nvec * VEC;
+    const bool has_x0 = s.has_x0 != 0;
+    const bool has_x = has_x0 && s.x_in != nullptr;
+    const bool has_o1 = has_x0 && s.out1 != nullptr;
+    const int n_pre = has_x0 ? 1 + (has_o1 ? 1 : 0) + (has_x ? 1 : 0) : 0; // sources ahead of the terms
+
+    if (tid == 0) {
+        for (int st = 0; st < stages; ++st) {
+            mbar_init(&full[st], 1);
+            mbar_init(&empty[st], TMA_CONSUMERS / 32);
         }
-        // full, converged warp inside one sample: butterfly + one atomic; otherwise (tail warp,
-        // warp straddling a sample boundary) one atomic per lane.
-        const unsigned mask = __activemask();
-        bool fast = mask == 0xffffffffu;
-        if (fast) {
-            const long long s0 = __shfl_sync(0xffffffffu, (long long)sample, 0);
-            fast = __all_sync(0xffffffffu, (long long)sample == s0);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= TMA_CONSUMERS) {
+        // ---------------- producer warp: lane i owns source i
+        const int lane = tid - TMA_CONSUMERS;
+        const unsigned char *gbase = nullptr;
+        bool is_out = false;
+        if (lane < n_src) {
+            if (lane < n_pre) {
+                if (lane == 0) { gbase = static_cast<const unsigned char *>(s.out0); is_out = true; }
+                else if (has_o1 && lane == 1) { gbase = static_cast<const unsigned char *>(s.out1); is_out = true; }
+                else gbase = static_cast<const unsigned char *>(s.x_in);
+            } else {
+                gbase = static_cast<const unsigned char *>(tab.ptr[lane - n_pre]);
+            }
         }
-        if (fast) {
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = (int)(it % stages);
+            const uint32_t ph = (uint32_t)((it / stages) & 1);
+            const int64_t e0 = tile * TILE_ELEMS;
+            const int64_t rem = numel - e0;
+            const uint32_t bytes = (uint32_t)((rem < TILE_ELEMS ? rem : TILE_ELEMS) * (int64_t)sizeof(T));
+            if (lane == 0) {
+                mbar_wait(&empty[st], ph ^ 1u);
+                mbar_expect_tx(&full[st], bytes * (uint32_t)n_src);
+            }
+            __syncwarp();
+            if (lane < n_src) {
+                int64_t off = e0;
+                if (is_out && s.out_strided) { // tiles never straddle samples (host guarantees per_sample % TILE_ELEMS == 0)
+                    const int64_t smp = e0 / s.per_sample;
+                    off = smp * s.out_sample_stride + (e0 - smp * s.per_sample);
+                }
+                bulk_g2s(tiles + ((size_t)st * n_src + lane) * TMA_TILE_BYTES, gbase + off * (int64_t)sizeof(T), bytes, &full[st]);
+            }
+        }
+    } else {
+        // ---------------- consumers
+        int64_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = (int)(it % stages);
+            const uint32_t ph = (uint32_t)((it / stages) & 1);
+            const int64_t e = tile * TILE_ELEMS + (int64_t)tid * VEC;
+            const bool valid = e < numel;
+            mbar_wait(&full[st], ph);
+            const unsigned char *sp = tiles + (size_t)st * n_src * TMA_TILE_BYTES + tid * 16;
+            Raw<T, VEC> rx, ro0, ro1;
+            float acc[VEC];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(s.sumsq + sample, ss);
-        } else {
-            atomicAdd(s.sumsq + sample, ss);
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+            if (valid) {
+                auto lds = [&](int src) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sp + (size_t)src * TMA_TILE_BYTES);
+                    Raw<T, VEC> r;
+                    r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+                    return r;
+                };
+                if (has_x0) {
+                    ro0 = lds(0);
+                    if (has_o1) ro1 = lds(1);
+                    if (has_x) rx = lds(n_pre - 1);
+                }
+                const int n = s.n_terms;
+                int t = 0;
+                for (; t + 4 <= n; t += 4) {
+                    Raw<T, VEC> rr[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rr[j] = lds(n_pre + t + j);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) fma_term<T, VEC>(acc, rr[j], tab.c[t + j]);
+                }
+                for (; t < n; ++t) fma_term<T, VEC>(acc, lds(n_pre + t), tab.c[t]);
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]); // stage is free as soon as it sits in registers
+            if (valid) {
+                int64_t sample = 0;
+                if (s.sumsq != nullptr) sample = e / s.per_sample;
+                step_epilogue<T, T, VEC>(s, e, sample, acc, ro0, ro1, rx, has_x0, has_x, has_o1);
+            }
         }
     }
 }
@@ -549,9 +718,65 @@ int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
     return check_launch("ni_step launch");
 }
 
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+// TMA variant: eligible when the row fits one shared-memory stage set and tiles map 1:1 onto sources
+template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cudaStream_t st, bool *used)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int TILE_ELEMS = TMA_TILE_BYTES / (int)sizeof(T);
+    *used = false;
+    const int n_pre = d->has_x0 ? 1 + (d->out1 != nullptr ? 1 : 0) + (a.x_in != nullptr ? 1 : 0) : 0;
+    const int n_src = n_pre + d->n_terms;
+    if (n_src < 1 || n_src > TMA_MAX_SRC || d->n_terms > 32 || d->accumulate) return NI_OK;
+    if (a.out_strided && d->per_sample % TILE_ELEMS != 0) return NI_OK;
+    const int ctas = g_tma_ctas_per_sm.load() < 1 ? 1 : g_tma_ctas_per_sm.load();
+    const int budget = g_tma_smem_kb.load() * 1024 / ctas - TMA_BAR_BYTES;
+    int stages = budget / (n_src * TMA_TILE_BYTES);
+    if (stages > g_tma_max_stages.load()) stages = g_tma_max_stages.load();
+    if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
+    if (stages < 2) return NI_OK;
+    const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TMA_TILE_BYTES;
+    static thread_local int attr_dev = -1; // the opt-in is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != attr_dev) {
+        cudaError_t err = cudaFuncSetAttribute(ni_step_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (err != cudaSuccess) return fail(NI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+        attr_dev = dev;
+    }
+    a.nvec = d->numel / VEC;
+    const int64_t ntiles = (d->numel + TILE_ELEMS - 1) / TILE_ELEMS;
+    int64_t grid = (int64_t)sm_count() * ctas;
+    if (grid > ntiles) grid = ntiles;
+    TermTable<32> tab;
+    memset(&tab, 0, sizeof(tab));
+    for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
+    ni_step_tma_kernel<T><<<(unsigned)grid, TMA_THREADS, smem, st>>>(a, tab, n_src, stages, ntiles);
+    *used = true;
+    return check_launch("ni_step (TMA) launch");
+}
+
 template <typename T, typename TO> int launch_step(StepArgs &a, const NiStepDesc *d, bool vec_ok, cudaStream_t st)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
+    if constexpr (std::is_same<T, TO>::value) {
+        if (vec_ok && g_variant.load() == 2) {
+            bool used = false;
+            const int rc = launch_step_tma<T>(a, d, st, &used);
+            if (rc != NI_OK || used) return rc;
+        }
+    }
     if (vec_ok) {
         a.nvec = d->numel / VEC;
         return launch_step_cap<T, TO, VEC>(a, d, st);
@@ -567,6 +792,16 @@ extern "C" {
 int ni_version(void) { return NI_ABI_VERSION; }
 const char *ni_last_error(void) { return g_err; }
 int64_t ni_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ni_set_option(const char *name, int value)
+{
+    if (name == nullptr) return fail(NI_ERR_INVALID, "ni_set_option: NULL name");
+    if (!strcmp(name, "variant")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "variant must be 0..2"); g_variant = value; return NI_OK; }
+    if (!strcmp(name, "tma_max_stages")) { if (value < 2 || value > TMA_MAX_STAGES) return fail(NI_ERR_INVALID, "tma_max_stages must be 2..%d", TMA_MAX_STAGES); g_tma_max_stages = value; return NI_OK; }
+    if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
+    if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
+    return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);
+}
 
 int ni_step(const NiStepDesc *d, void *stream)
 {

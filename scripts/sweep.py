@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Run bench.py over kernel variants / options on the GPU box and print one compact line each.
+usage: scripts/sweep.py [--lib path.so ...]   (each --lib is an alternative build of libni_b200.so)"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNS = [
+    ("c2", ["--variant", "1"]),
+    ("c2", ["--variant", "2"]),
+    ("c2", ["--variant", "2", "--opt", "tma_ctas_per_sm=2"]),
+    ("c2", ["--variant", "2", "--opt", "tma_max_stages=3"]),
+    ("c2", ["--variant", "2", "--opt", "tma_max_stages=4"]),
+    ("c3", ["--variant", "1"]),
+    ("c3", ["--variant", "2"]),
+    ("c3", ["--variant", "2", "--opt", "tma_ctas_per_sm=2"]),
+    ("c3", ["--variant", "2", "--opt", "tma_max_stages=4"]),
+]
+libs = [a for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--lib"] or [None]
+if "--ldg-only" in sys.argv:
+    RUNS = [("c2", ["--variant", "1"]), ("c3", ["--variant", "1"])]
+out = []
+for lib in libs:
+    for cfg, extra in RUNS:
+        env = dict(os.environ)
+        if lib:
+            env["NI_B200_LIB"] = os.path.abspath(lib)
+        steps = "1500" if cfg == "c2" else "300"
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", cfg, "--steps", steps, "--warmup", "20", "--no-cpu-baseline", "--no-e2e"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        try:
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            line = f"{os.path.basename(lib) if lib else 'default':28s} {cfg} {' '.join(extra):42s} ms/traj={j['ms_per_step']:.4f} GB/s={j['roofline']['achieved']:.0f} frac={j['roofline']['frac']:.3f} sm_mhz={j['clocks']['sm_mhz']}"
+        except Exception as e:  # noqa: BLE001
+            line = f"{lib} {cfg} {extra} FAILED: {r.stderr[-400:]}"
+        print(line, flush=True)
+        out.append(line)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+open(os.path.join(ROOT, "gpurun_out", "sweep.txt"), "a").write("\n".join(out) + "\n")
