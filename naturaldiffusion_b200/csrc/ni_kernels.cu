@@ -48,7 +48,8 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 // tuning knobs (ni_set_option): which step kernel, and the TMA kernel's geometry
 std::atomic<int> g_variant{0};       // 0 auto, 1 always the LDG kernel, 2 the TMA kernel whenever eligible
-std::atomic<int> g_tma_max_stages{8};
+std::atomic<int> g_tma_max_stages{32};
+std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
 std::atomic<int> g_tma_ctas_per_sm{1};
 
@@ -432,17 +433,20 @@ __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const 
 }
 
 // ---- variant 2: TMA bulk copies into a shared-memory ring, warp-specialised -------------------------
-// One persistent CTA per SM: a producer warp streams [source][tile] slabs global->shared with
-// cp.async.bulk (one lane per source tensor, completion on an mbarrier), 256 consumer threads read their
-// 16 B of every source from shared memory, run the same epilogue, and store straight to global.
-// 4 KB per source per stage; STAGES x n_src x 4 KB (<= ~200 KB) of loads are in flight per SM regardless
-// of register pressure.  Source order in a stage: out0, [out1], [x_in], term 0..n-1.
-constexpr int TMA_CONSUMERS = 256;
-constexpr int TMA_THREADS = TMA_CONSUMERS + 32;
-constexpr int TMA_TILE_BYTES = TMA_CONSUMERS * 16;
-constexpr int TMA_MAX_STAGES = 8;
-constexpr int TMA_MAX_SRC = 24;
-constexpr int TMA_BAR_BYTES = 128;
+// Persistent CTAs (one per SM by default): a producer warp streams [source][tile] slabs global->shared with
+// cp.async.bulk (one lane per source tensor, completion counted on an mbarrier), NW consumer warps each own
+// whole tiles (TMA_TILE_BYTES per source = 4 vectors per lane), so consumer warps run decoupled from each
+// other with 4 independent accumulation chains per thread.  A consumer reads the stored terms from shared
+// memory, runs the same epilogue as the direct-load kernel (reading out0/out1/x_k from shared memory when it
+// needs them), stores straight to global and hands the stage back.  stages x n_src x 2 KB (<= ~200 KB) of
+// loads are in flight per SM regardless of register pressure.  Source order in a stage: out0, [out1], [x_k],
+// term 0..n-1.
+constexpr int TMA_TILE_BYTES = 2048;
+constexpr int TMA_VPL = TMA_TILE_BYTES / 16 / 32; // vectors per consumer lane per tile
+constexpr int TMA_MAX_WARPS = 16;
+constexpr int TMA_MAX_STAGES = 32;
+constexpr int TMA_MAX_SRC = 32;
+constexpr int TMA_BAR_BYTES = 2 * TMA_MAX_STAGES * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -461,7 +465,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
 }
 
 template <typename T>
-__global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<32> tab, int n_src, int stages, int64_t ntiles)
+__global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<32> tab, int n_src, int stages, int64_t ntiles)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int TILE_ELEMS = TMA_TILE_BYTES / (int)sizeof(T);
@@ -470,6 +474,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __gri
     uint64_t *empty = full + TMA_MAX_STAGES;
     unsigned char *tiles = smem + TMA_BAR_BYTES;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nw = (int)(blockDim.x >> 5) - 1; // consumer warps; the last warp is the producer
     const int64_t numel = s.nvec * VEC;
     const bool has_x0 = s.has_x0 != 0;
     const bool has_x = has_x0 && s.x_in != nullptr;
@@ -479,15 +485,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __gri
     if (tid == 0) {
         for (int st = 0; st < stages; ++st) {
             mbar_init(&full[st], 1);
-            mbar_init(&empty[st], TMA_CONSUMERS / 32);
+            mbar_init(&empty[st], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid >= TMA_CONSUMERS) {
+    if (warp == nw) {
         // ---------------- producer warp: lane i owns source i
-        const int lane = tid - TMA_CONSUMERS;
         const unsigned char *gbase = nullptr;
         bool is_out = false;
         if (lane < n_src) {
@@ -499,10 +504,9 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __gri
                 gbase = static_cast<const unsigned char *>(tab.ptr[lane - n_pre]);
             }
         }
-        int64_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int st = (int)(it % stages);
-            const uint32_t ph = (uint32_t)((it / stages) & 1);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t e0 = tile * TILE_ELEMS;
             const int64_t rem = numel - e0;
             const uint32_t bytes = (uint32_t)((rem < TILE_ELEMS ? rem : TILE_ELEMS) * (int64_t)sizeof(T));
@@ -519,51 +523,55 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) ni_step_tma_kernel(const __gri
                 }
                 bulk_g2s(tiles + ((size_t)st * n_src + lane) * TMA_TILE_BYTES, gbase + off * (int64_t)sizeof(T), bytes, &full[st]);
             }
+            if (++st == stages) { st = 0; ph ^= 1u; }
         }
     } else {
-        // ---------------- consumers
-        int64_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        // ---------------- consumer warp `warp` owns tiles it = warp, warp + nw, ... of this CTA's sequence
+        const int n = s.n_terms;
+        for (int64_t it = warp;; it += nw) {
+            const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
+            if (tile >= ntiles) break;
             const int st = (int)(it % stages);
             const uint32_t ph = (uint32_t)((it / stages) & 1);
-            const int64_t e = tile * TILE_ELEMS + (int64_t)tid * VEC;
-            const bool valid = e < numel;
+            const int64_t e_tile = tile * TILE_ELEMS;
             mbar_wait(&full[st], ph);
-            const unsigned char *sp = tiles + (size_t)st * n_src * TMA_TILE_BYTES + tid * 16;
-            Raw<T, VEC> rx, ro0, ro1;
-            float acc[VEC];
+            const unsigned char *sp = tiles + (size_t)st * n_src * TMA_TILE_BYTES + lane * 16;
+            auto lds = [&](int src, int v) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(sp + (size_t)src * TMA_TILE_BYTES + v * 512);
+                Raw<T, VEC> r;
+                r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+                return r;
+            };
+            float acc[TMA_VPL][VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-            if (valid) {
-                auto lds = [&](int src) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(sp + (size_t)src * TMA_TILE_BYTES);
-                    Raw<T, VEC> r;
-                    r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
-                    return r;
-                };
-                if (has_x0) {
-                    ro0 = lds(0);
-                    if (has_o1) ro1 = lds(1);
-                    if (has_x) rx = lds(n_pre - 1);
+            for (int v = 0; v < TMA_VPL; ++v)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[v][i] = 0.f;
+            for (int t = 0; t < n; ++t) {
+                const float c = tab.c[t];
+                Raw<T, VEC> rr[TMA_VPL];
+#pragma unroll
+                for (int v = 0; v < TMA_VPL; ++v) rr[v] = lds(n_pre + t, v);
+#pragma unroll
+                for (int v = 0; v < TMA_VPL; ++v) fma_term<T, VEC>(acc[v], rr[v], c);
+            }
+#pragma unroll
+            for (int v = 0; v < TMA_VPL; ++v) {
+                const int64_t e = e_tile + (int64_t)(v * 32 + lane) * VEC;
+                if (e < numel) {
+                    Raw<T, VEC> rx, ro0, ro1;
+                    if (has_x0) {
+                        ro0 = lds(0, v);
+                        if (has_o1) ro1 = lds(1, v);
+                        if (has_x) rx = lds(n_pre - 1, v);
+                    }
+                    int64_t sample = 0;
+                    if (s.sumsq != nullptr) sample = e / s.per_sample;
+                    step_epilogue<T, T, VEC>(s, e, sample, acc[v], ro0, ro1, rx, has_x0, has_x, has_o1);
                 }
-                const int n = s.n_terms;
-                int t = 0;
-                for (; t + 4 <= n; t += 4) {
-                    Raw<T, VEC> rr[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) rr[j] = lds(n_pre + t + j);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) fma_term<T, VEC>(acc, rr[j], tab.c[t + j]);
-                }
-                for (; t < n; ++t) fma_term<T, VEC>(acc, lds(n_pre + t), tab.c[t]);
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[st]); // stage is free as soon as it sits in registers
-            if (valid) {
-                int64_t sample = 0;
-                if (s.sumsq != nullptr) sample = e / s.per_sample;
-                step_epilogue<T, T, VEC>(s, e, sample, acc, ro0, ro1, rx, has_x0, has_x, has_o1);
-            }
+            if (lane == 0) mbar_arrive(&empty[st]);
         }
     }
 }
@@ -740,12 +748,15 @@ template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cuda
     const int n_src = n_pre + d->n_terms;
     if (n_src < 1 || n_src > TMA_MAX_SRC || d->n_terms > 32 || d->accumulate) return NI_OK;
     if (a.out_strided && d->per_sample % TILE_ELEMS != 0) return NI_OK;
-    const int ctas = g_tma_ctas_per_sm.load() < 1 ? 1 : g_tma_ctas_per_sm.load();
+    const int ctas = g_tma_ctas_per_sm.load();
+    int nw = g_tma_warps.load();
     const int budget = g_tma_smem_kb.load() * 1024 / ctas - TMA_BAR_BYTES;
     int stages = budget / (n_src * TMA_TILE_BYTES);
     if (stages > g_tma_max_stages.load()) stages = g_tma_max_stages.load();
     if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
     if (stages < 2) return NI_OK;
+    if (nw > stages) nw = stages;      // a consumer warp without a stage of its own would only wait
+    stages -= stages % nw;             // stage of tile `it` is it % stages; keep it aligned with the warp owning it
     const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TMA_TILE_BYTES;
     static thread_local int attr_dev = -1; // the opt-in is per device
     int dev = 0;
@@ -762,7 +773,7 @@ template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cuda
     TermTable<32> tab;
     memset(&tab, 0, sizeof(tab));
     for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-    ni_step_tma_kernel<T><<<(unsigned)grid, TMA_THREADS, smem, st>>>(a, tab, n_src, stages, ntiles);
+    ni_step_tma_kernel<T><<<(unsigned)grid, (nw + 1) * 32, smem, st>>>(a, tab, n_src, stages, ntiles);
     *used = true;
     return check_launch("ni_step (TMA) launch");
 }
@@ -798,6 +809,7 @@ int ni_set_option(const char *name, int value)
     if (name == nullptr) return fail(NI_ERR_INVALID, "ni_set_option: NULL name");
     if (!strcmp(name, "variant")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "variant must be 0..2"); g_variant = value; return NI_OK; }
     if (!strcmp(name, "tma_max_stages")) { if (value < 2 || value > TMA_MAX_STAGES) return fail(NI_ERR_INVALID, "tma_max_stages must be 2..%d", TMA_MAX_STAGES); g_tma_max_stages = value; return NI_OK; }
+    if (!strcmp(name, "tma_warps")) { if (value < 1 || value > TMA_MAX_WARPS) return fail(NI_ERR_INVALID, "tma_warps must be 1..%d", TMA_MAX_WARPS); g_tma_warps = value; return NI_OK; }
     if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
     if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
     return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);

@@ -10,13 +10,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RUNS = [
     ("c2", ["--variant", "1"]),
     ("c2", ["--variant", "2"]),
-    ("c2", ["--variant", "2", "--opt", "tma_ctas_per_sm=2"]),
-    ("c2", ["--variant", "2", "--opt", "tma_max_stages=3"]),
-    ("c2", ["--variant", "2", "--opt", "tma_max_stages=4"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=4"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=12"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=16"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=2"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=4", "--opt", "tma_ctas_per_sm=2"]),
+    ("c2", ["--variant", "2", "--opt", "tma_warps=16", "--opt", "tma_smem_kb=120"]),
     ("c3", ["--variant", "1"]),
     ("c3", ["--variant", "2"]),
-    ("c3", ["--variant", "2", "--opt", "tma_ctas_per_sm=2"]),
-    ("c3", ["--variant", "2", "--opt", "tma_max_stages=4"]),
+    ("c3", ["--variant", "2", "--opt", "tma_warps=12"]),
+    ("c3", ["--variant", "2", "--opt", "tma_warps=16"]),
+    ("c3", ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=2"]),
 ]
 libs = [a for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--lib"] or [None]
 if "--ldg-only" in sys.argv:
