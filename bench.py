@@ -32,9 +32,12 @@ sys.path.insert(0, ROOT)
 
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "reference_weights")
 CONFIGS = {
-    # name: (matrix file, per-GPU batch, sample shape, model outputs)
-    "c2": ("step_10_weight_42.npz", 4096, (3, 32, 32), 1),
-    "c3": ("step_15_weight_173.npz", 16384, (3, 32, 32), 1),
+    # name: (matrix, per-GPU batch, sample shape, model outputs m, model-output channels, state dtype)
+    "c2": ("step_10_weight_42.npz", 4096, (3, 32, 32), 1, 3, "f32"),           # BASELINE configs[1] -- the bench headline
+    "c3": ("step_15_weight_173.npz", 16384, (3, 32, 32), 1, 3, "f32"),         # configs[2]
+    "c4": ("ddpm_250 (generated)", 1024, (4, 32, 32), 2, 8, "f32"),            # configs[3]: DiT-XL/2 shapes, CFG, 8-channel outputs
+    "c5": ("sd3_step_28_weight.csv", 64, (16, 128, 128), 2, 16, "f16"),        # configs[4]: SD3 shapes, fp16 state
+    "c5s": ("sd3_step_28_weight_sharp.csv", 64, (16, 128, 128), 2, 16, "f16"),
 }
 METRIC = "NI-update samples/sec (HBM GB/s and % peak in `roofline`)"
 
@@ -42,8 +45,8 @@ METRIC = "NI-update samples/sec (HBM GB/s and % peak in `roofline`)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed trajectories (default: ~2 s worth for ours, 10 for --impl reference)")
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
@@ -53,35 +56,51 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--markov", default="auto", choices=["auto", "0", "1"], help="first-order fast path (c4/c5): auto|0|1")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 10 if args.impl == "reference" else {"c2": 4000, "c3": 500, "c4": 8, "c5": 40, "c5s": 40}[args.config]
+    if args.warmup is None:
+        args.warmup = 1 if args.impl == "reference" else (20 if args.config in ("c2", "c3") else 3)
+    return args
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference loop, null denoiser
 # ----------------------------------------------------------------------------------------------
-def cpu_trajectory(A, B, node, noise, h):
-    """Reference arithmetic (oracle restatement) for one batch; `h` plays the raw net output."""
+def make_cpu_trajectory(cfg, batch):
+    """Reference arithmetic (oracle restatement, reference dtypes) for one batch with the null denoiser.
+    c2/c3: src/CIFAR10NaturalInference.py:294-304; c4: src/ValidateNaturalInference.py:349-366;
+    c5: src/SD3NaturalInference.py:201-221 (in fp32: fp16 elementwise on a CPU is not representative)."""
     import torch
     from oracle import ni_oracle as O
-    score_fn = O.make_vp_score_fn(lambda x, labels: h)
-    x, _ = O.cifar_ni_loop(A, B, node, score_fn, noise)
-    return x
+    fname, _, shape, m, cout, _ = CONFIGS[cfg]
+    g = torch.Generator().manual_seed(888)
+    noise = torch.randn((batch,) + shape, generator=g)
+    outs = [torch.randn((batch, cout) + shape[1:], generator=g) for _ in range(m)]
+    if cfg in ("c2", "c3"):
+        A, B, node = O.load_triple(os.path.join(WEIGHTS, fname))
+        score_fn = O.make_vp_score_fn(lambda x, labels: outs[0])
+        return lambda: O.cifar_ni_loop(A, B, node, score_fn, noise)[0]
+    if cfg == "c4":
+        A, B, node = O.ddpm_triple(250)
+        fresh = [torch.randn((batch,) + shape, generator=g) for _ in range(4)]
+        fresh = [fresh[k % 4] for k in range(250)]  # distinct values are irrelevant for timing; 250 tensors would only cost RAM
+        eps_model = lambda z, t: (outs[0][:, :4], outs[1][:, :4])
+        return lambda: O.validate_ni_loop(A, B, node, eps_model, noise, fresh)[0]
+    W = O.load_sd3_csv(os.path.join(WEIGHTS, fname))
+    sig = O.sd3_sigmas()
+    return lambda: O.sd3_ni_loop(W, sig, lambda x, k: (outs[0], outs[1]), noise)[0]
 
 
 def time_cpu(cfg, batch, reps, warm):
-    import torch
-    from oracle import ni_oracle as O
-    fname, _, shape, _ = CONFIGS[cfg]
-    A, B, node = O.load_triple(os.path.join(WEIGHTS, fname))
-    g = torch.Generator().manual_seed(888)
-    noise = torch.randn((batch,) + shape, generator=g)
-    h = torch.randn((batch,) + shape, generator=g)
+    fn = make_cpu_trajectory(cfg, batch)
     for _ in range(warm):
-        cpu_trajectory(A, B, node, noise, h)
+        fn()
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_trajectory(A, B, node, noise, h)
+        fn()
         ts.append(time.perf_counter() - t0)
     return ts
 
@@ -102,12 +121,15 @@ def run_reference(args, rank):
         return
     import torch
     cores = torch.get_num_threads()
-    fname, full_batch, shape, m = CONFIGS[args.config]
-    # bounded sample: size the batch so (steps+warmup) trajectories take about two minutes
-    probe = time_cpu(args.config, 128, 1, 1)[0]
+    fname, full_batch, shape, m, cout, _ = CONFIGS[args.config]
+    # bounded sample: the full per-GPU batch when (steps+warmup) trajectories of it fit in about two minutes,
+    # otherwise the largest batch that does (time is super-linear in the batch once tensors leave the CPU caches)
+    pb = min(full_batch, 64)
+    probe = time_cpu(args.config, pb, 1, 1)[0]
     budget = 120.0 / max(1, args.steps + args.warmup)
-    batch = int(max(64, min(full_batch, 128 * budget / probe)))
-    batch -= batch % 64
+    batch = int(max(8, min(full_batch, pb * budget / probe / 4)))
+    if batch >= 64:
+        batch -= batch % 64
     ts = time_cpu(args.config, batch, args.steps, args.warmup)
     total = sum(ts)
     val = batch * args.steps / total
@@ -115,7 +137,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 history / f32 state (reference dtypes)", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {fname} update-only, null denoiser, sample of {batch} of {full_batch} samples per step",
+        "config": {"workload": f"{args.config}: {fname} NI update-only, null denoiser, sample of {batch} of {full_batch} samples per step",
                    "shape": [batch] + list(shape)},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": f"{batch}-sample batches x {args.steps} trajectories; torch {torch.__version__} CPU; {cpu_model()}"},
@@ -205,19 +227,35 @@ def run_ours(args, rank, world, local_rank):
     for kv in args.opt:
         name, val = kv.split("=")
         nilib.set_option(name, int(val))
-    fname, batch, shape, m = CONFIGS[args.config]
-    batch = args.batch or batch
-    triple = ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, fname))
-    K = triple.K
-    sampler = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), batch, shape, device=dev, seed=888,
-                                      eps0=args.eps0, sample_offset=rank * batch)
+    from naturaldiffusion_b200 import coeffs, generators
     from naturaldiffusion_b200.ops import philox_normal
-    h = philox_normal((batch,) + shape, seed=888, tensor_id=1000, elem_offset=sampler.elem_offset, device=dev)  # null denoiser output
-    den = lambda x, k: h
+    fname, batch, shape, m, cout, dts = CONFIGS[args.config]
+    batch = args.batch or batch
+    dtype = {"f32": torch.float32, "f16": torch.float16}[dts]
+    markov = {"auto": "auto", "0": False, "1": True}[args.markov]
+    if args.config in ("c2", "c3"):
+        triple = ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, fname))
+        io = ni.io_score_vp(triple.node)
+    elif args.config == "c4":
+        triple = generators.ddpm_triple(250)
+        c1, c2, _ = coeffs.ddim_x0_coeffs(250)
+        io = ni.io_eps_cfg(c1, c2, 4.0)
+    else:
+        sig = coeffs.flow_match_sigmas(28)
+        triple = ni.CoeffTriple.from_sd3_csv(os.path.join(WEIGHTS, fname), sig)
+        io = ni.io_velocity_cfg(sig, 7.0)
+    K = triple.K
+    sampler = NaturalInferenceSampler(triple, io, batch, shape, device=dev, dtype=dtype, seed=888,
+                                      eps0=args.eps0, sample_offset=rank * batch, markov=markov)
+    # null denoiser: m pre-generated N(0,1) model-output tensors [B, cout, H, W], re-read from HBM every step
+    outs = tuple(philox_normal((batch, cout) + shape[1:], seed=888, tensor_id=1000 + i, elem_offset=rank * batch * cout * shape[1] * shape[2],
+                               dtype=dtype, device=dev) for i in range(m))
+    den = (lambda x, k: outs[0]) if m == 1 else (lambda x, k: outs)
     numel = sampler.numel
+    esize = torch.empty(0, dtype=dtype).element_size()
     stored0 = args.eps0 == "stored"
     units = sampler.plan.total_units(m, eps0_stored=stored0)
-    bytes_per_traj = units * numel * 4
+    bytes_per_traj = units * numel * esize
     launches_per_traj = sampler.kernel_launches_per_trajectory
 
     def barrier():
@@ -226,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident arm
-    noise = philox_normal((batch,) + shape, seed=888, tensor_id=0, elem_offset=sampler.elem_offset, device=dev)
+    noise = philox_normal((batch,) + shape, seed=888, tensor_id=0, elem_offset=sampler.elem_offset, dtype=dtype, device=dev)
     c0 = ni.launch_count()
     sampler.sample(den, noise=noise)
     torch.cuda.synchronize()
@@ -263,19 +301,20 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end arm: host buffers through the public sampler API
     e2e = None
     if not args.no_e2e:
-        noise_h = torch.empty((batch,) + shape, dtype=torch.float32).pin_memory()
+        pixels = args.config in ("c2", "c3")  # image-space configs end in the uint8 stage; latent configs return the latent
+        noise_h = torch.empty((batch,) + shape, dtype=dtype).pin_memory()
         noise_h.copy_(noise)
-        out_h = torch.empty((batch, shape[1], shape[2], shape[0]), dtype=torch.uint8).pin_memory()
-        e2e_sampler = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), batch, shape, device=dev, seed=888,
-                                              sample_offset=rank * batch)
+        out_h = (torch.empty((batch, shape[1], shape[2], shape[0]), dtype=torch.uint8) if pixels else torch.empty((batch,) + shape, dtype=dtype)).pin_memory()
+        sampler._graph = None
+        e2e_sampler = sampler  # same state slab; launches go through the non-graph path with the H2D / D2H copies in stream order
         for _ in range(3):
-            e2e_sampler.sample_host(den, noise_h, out_h, pixels=True)
+            e2e_sampler.sample_host(den, noise_h, out_h, pixels=pixels)
         barrier()
-        n_e2e = max(10, args.steps // 4)
+        n_e2e = max(3, args.steps // 4)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(n_e2e):
-            e2e_sampler.sample_host(den, noise_h, out_h, pixels=True)
+            e2e_sampler.sample_host(den, noise_h, out_h, pixels=pixels)
         s1.record()
         barrier()
         ems = s0.elapsed_time(s1)
@@ -283,9 +322,9 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = t.item()
-        e2e = {"value": world * batch * n_e2e / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": noise_h.numel() * 4,
-               "d2h_bytes_per_step": out_h.numel(), "steps": n_e2e, "ms_per_step": ems / n_e2e,
-               "api": "NaturalInferenceSampler.sample_host(pixels=True): pinned fp32 noise in, NHWC uint8 out"}
+        e2e = {"value": world * batch * n_e2e / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": noise_h.numel() * noise_h.element_size(),
+               "d2h_bytes_per_step": out_h.numel() * out_h.element_size(), "steps": n_e2e, "ms_per_step": ems / n_e2e,
+               "api": f"NaturalInferenceSampler.sample_host(pixels={pixels}): pinned {dts} noise in, " + ("NHWC uint8 out" if pixels else f"{dts} latent out")}
 
     if rank != 0:
         if world > 1:
@@ -294,27 +333,28 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cb = 1024
-        ts = time_cpu(args.config, cb, 3, 1)
+        cb = {"c2": batch, "c3": 4096, "c4": 32, "c5": 4, "c5s": 4}[args.config]
+        ts = time_cpu(args.config, cb, 2, 1)
         cpu = {"value": cb / min(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{cb}-sample batch of the same workload, best of 3 trajectories after 1 warm-up ({sum(ts):.1f} s CPU work); "
-                         f"torch {torch.__version__} CPU, {cpu_model()}"}
+               "sample": f"{cb}-sample batch of the same workload (full per-GPU batch is {batch}), best of 2 trajectories after 1 warm-up "
+                         f"({sum(ts):.1f} s CPU work); oracle port of the reference loop in the reference's dtypes; torch {torch.__version__} CPU, {cpu_model()}"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dts,
         "data": "synthetic",
-        "config": {"workload": f"{args.config}: CIFAR-10 32x32 NI update, {fname}, batch {batch}/GPU, K={K} fused steps per trajectory, "
-                               f"null denoiser (pre-generated N(0,1) model output re-read from HBM each step)",
+        "config": {"workload": f"{args.config}: NI update, {fname}, batch {batch}/GPU x {list(shape)}, K={K} fused steps per trajectory, "
+                               f"null denoiser ({m} pre-generated N(0,1) model output(s) of {cout} channels re-read from HBM each step)",
+                   "markov_fast_path": bool(sampler.plan.markov),
                    "shape": [batch] + list(shape), "eps0": args.eps0, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
-                   "l2": f"inputs larger than L2: per-trajectory working set {sampler.state_bytes() / 1e6 + numel * 4 * 2 / 1e6:.0f} MB vs 126 MB L2",
+                   "l2": f"inputs larger than L2: per-trajectory working set {(sampler.state_bytes() + sum(o.numel() for o in outs) * esize) / 1e6:.0f} MB vs 126 MB L2",
                    "state_bytes": sampler.state_bytes()},
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": launches_per_traj * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args.config, args.eps0), "peak_source": peak_src,
-                     "kernel": "ni_step_kernel<float,float,4,32>", "algorithmic_bytes_per_launch": bytes_per_traj / launches_per_traj,
+                     "kernel": "ni_step_kernel (direct-load)" if args.variant != 2 else "ni_step_tma_kernel", "algorithmic_bytes_per_launch": bytes_per_traj / launches_per_traj,
                      "tensor_transfers_per_trajectory": units, "us_per_launch": 1e3 * ms_per_step / launches_per_traj,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NI_ABI_VERSION 1
+#define NI_ABI_VERSION 2
 #define NI_MAX_TERMS 512 /* stored history/noise terms per launch; longer rows: call twice with accumulate */
 #define NI_MAX_GEN 4     /* noise terms generated in-kernel per launch */
 
@@ -54,6 +54,7 @@ enum {
  *     x0      = a * x_in + b0 * out0 + b1 * out1                 (model I/O scaling + CFG)
  *     x_next  = c_x0 * x0 + sum_t term_coeffs[t] * term[t]        (row k of A against the x0 ring,
  *             + sum_g gen_coeffs[g] * N(seed, gen_tensor_ids[g])   row k of B against stored / fresh noise)
+ *             + c_xin * x_in                                       (first-order rows only, see c_xin)
  * in ONE pass over HBM.  Replaces, per step,
  *   src/CIFAR10NaturalInference.py:298-304 (data_fn :219-230 + weighted_sum :233-238 + noise mix),
  *   src/ValidateNaturalInference.py:352-366 (CFG fuse :193, x0 :355, randn_like :359, 2x weighted_sum :198-204),
@@ -75,6 +76,9 @@ typedef struct NiStepDesc {
     float a, b0, b1;
     void *x0_dst;              /* ring slot receiving x0_k, or NULL if no later row reads it */
     float c_x0;                /* A[k,k] */
+    float c_xin;               /* usually 0.  Rows of first-order samplers (DDPM, DDIM, Euler, flow Euler) satisfy
+                                  row_k[:k] = c_k * row_{k-1}[:k], i.e. sum_{j<k} A[k,j] x0_j + sum_{j<=k} B[k,j] eps_j
+                                  = c_k * x_k: pass c_k here and no history terms -- O(1) reads per step */
 
     int32_t n_terms;           /* stored terms: earlier x0 slots and stored noise tensors */
     const void *const *term_ptrs_host; /* HOST array[n_terms] of device pointers */

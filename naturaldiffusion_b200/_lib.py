@@ -13,7 +13,7 @@ import os
 NI_F32, NI_F16, NI_BF16, NI_F64 = 0, 1, 2, 3
 NI_MAX_TERMS = 512
 NI_MAX_GEN = 4
-NI_ABI_VERSION = 1
+NI_ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NI_B200_LIB", os.path.join(_HERE, "libni_b200.so"))
@@ -40,6 +40,7 @@ class NiStepDesc(C.Structure):
         ("b1", C.c_float),
         ("x0_dst", C.c_void_p),
         ("c_x0", C.c_float),
+        ("c_xin", C.c_float),
         ("n_terms", C.c_int32),
         ("term_ptrs_host", C.POINTER(C.c_void_p)),
         ("term_coeffs_host", C.POINTER(C.c_float)),

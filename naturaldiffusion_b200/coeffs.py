@@ -177,6 +177,7 @@ class StepPlanEntry:
     keep_fresh: bool                       # a later row reads eps_{k+1}
     x0_slot: int = -1
     fresh_slot: int = -1
+    c_xin: float = 0.0                     # Markov rows: coefficient of x_k standing for the whole history
 
 
 @dataclass
@@ -185,6 +186,7 @@ class StepPlan:
     steps: List[StepPlanEntry]
     n_x0_slots: int
     n_eps_slots: int                       # slots for eps_j, j >= 1 (eps_0 is separate)
+    markov: bool = False                   # rows collapsed onto c_k * x_k (first-order samplers)
     x0_slot_of: List[int] = field(default_factory=list)
     eps_slot_of: List[int] = field(default_factory=list)   # index j (0 unused)
     eps0_last_use: int = -1
@@ -228,8 +230,58 @@ def _alloc_slots(produce_step: Sequence[int], last_use: Sequence[int]):
     return slot, len(free_at)
 
 
-def build_plan(triple: CoeffTriple, keep_all_x0: bool = False) -> StepPlan:
+def markov_ratios(triple: CoeffTriple, tol: float = 1e-12):
+    """First-order structure of the x0 part.  If every row satisfies A[k,:k] = c_k * A[k-1,:k] (DDPM, DDIM,
+    Euler-Maruyama, probability-flow Euler, flow-matching Euler, the default SD3 table) return (c, R) where
+        sum_{j<k} A[k,j] x0_j + sum_{j<=k} B[k,j] eps_j  =  c_k * x_k + sum_{j<=k} R[k,j] eps_j,
+        R[k,j] = B[k,j] - c_k * B[k-1,j]     (row -1 := the unit vector on eps_0, because x_0 = eps_0)
+    so a step needs no x0 history at all, and noise only where R is non-zero (nowhere for exact first-order
+    samplers; eps_0 for the 2-decimal SD3 table).  Returns None when the x0 part is not first-order."""
     A, B, K = triple.A, triple.B, triple.K
+    cs, R = [], np.zeros((K, K + 1))
+    prev_b = np.zeros(K + 1)
+    prev_b[0] = 1.0
+    for k in range(K):
+        prev_a, cur_a = (A[k - 1, :k], A[k, :k]) if k > 0 else (np.zeros(0), np.zeros(0))
+        nz = np.abs(prev_a) > 0
+        if nz.any():
+            c = float(np.median(cur_a[nz] / prev_a[nz]))
+        else:  # no x0 column to pin the ratio: take it from the noise part
+            nzb = np.abs(prev_b[: k + 1]) > 0
+            c = float(np.median(B[k, : k + 1][nzb] / prev_b[: k + 1][nzb])) if nzb.any() else 0.0
+        if k > 0 and np.abs(cur_a - c * prev_a).max(initial=0.0) > tol * max(1.0, np.abs(cur_a).max(initial=0.0)):
+            return None
+        r = B[k, : k + 1] - c * prev_b[: k + 1]
+        r[np.abs(r) <= tol * max(1.0, np.abs(B[k]).max())] = 0.0
+        R[k, : k + 1] = r
+        cs.append(c)
+        prev_b = B[k].copy()
+    return cs, R
+
+
+def build_plan(triple: CoeffTriple, keep_all_x0: bool = False, markov: bool = False) -> StepPlan:
+    A, B, K = triple.A, triple.B, triple.K
+    if markov:
+        mr = markov_ratios(triple)
+        if mr is None:
+            raise ValueError("the x0 part of the matrix is not first-order (Markov); build the plan with markov=False")
+        cs, R = mr
+        nzR = R != 0
+        eps_last = [max([k for k in range(K) if nzR[k, j]], default=-1) for j in range(K + 1)]
+        eps_slot_j, n_eps = _alloc_slots([j - 1 for j in range(1, K + 1)], eps_last[1:])
+        eps_slot = [-1] + eps_slot_j
+        x0_slot = list(range(K)) if keep_all_x0 else [-1] * K
+        steps = []
+        for k in range(K):
+            fresh = float(B[k, k + 1]) if B[k, k + 1] != 0 else None
+            keep_fresh = eps_last[k + 1] > k
+            if keep_fresh and fresh is None:
+                fresh = 0.0
+            steps.append(StepPlanEntry(k=k, c_x0=float(A[k, k]), hist=[], eps=[(j, float(R[k, j])) for j in range(k + 1) if nzR[k, j]],
+                                       fresh=fresh, keep_x0=keep_all_x0, keep_fresh=keep_fresh, x0_slot=x0_slot[k],
+                                       fresh_slot=eps_slot[k + 1], c_xin=cs[k]))
+        return StepPlan(K=K, steps=steps, n_x0_slots=K if keep_all_x0 else 0, n_eps_slots=n_eps, x0_slot_of=x0_slot,
+                        eps_slot_of=eps_slot, eps0_last_use=eps_last[0], markov=True)
     nzA = A != 0
     nzB = B != 0
     # last row that reads column j

@@ -287,7 +287,7 @@ struct StepArgs {
     uint64_t gen_tid[NI_MAX_GEN];
     uint64_t elem_offset;
     float gen_c[NI_MAX_GEN];
-    float a, b0, b1, c_x0;
+    float a, b0, b1, c_x0, c_xin;
     uint32_t k0, k1;
     int n_terms, n_gen;
     int has_x0, out_strided, accumulate, lp_dtype;
@@ -343,6 +343,12 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int6
         if (s.x0_dst != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x0_dst) + e, pack<T, VEC>(x0));
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s.c_x0, x0[i], acc[i]);
+        // first-order (Markov) rows: the whole history collapses into c_xin * x_k, which is already in registers
+        if (has_x && s.c_xin != 0.f) {
+            unpack<T, VEC>(rx, f);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s.c_xin, f[i], acc[i]);
+        }
     }
 
     // x_{k+1}
@@ -826,7 +832,7 @@ int ni_step(const NiStepDesc *d, void *stream)
     if (d->n_terms > 0 && (d->term_ptrs_host == nullptr || d->term_coeffs_host == nullptr)) return fail(NI_ERR_INVALID, "ni_step: term tables are NULL");
     if (d->has_x0) {
         if (d->out0 == nullptr) return fail(NI_ERR_INVALID, "ni_step: has_x0 but out0 is NULL");
-        if (d->x_in == nullptr && d->a != 0.f) return fail(NI_ERR_INVALID, "ni_step: a != 0 but x_in is NULL");
+        if (d->x_in == nullptr && (d->a != 0.f || d->c_xin != 0.f)) return fail(NI_ERR_INVALID, "ni_step: a or c_xin != 0 but x_in is NULL");
         if (d->out_sample_stride < d->per_sample) return fail(NI_ERR_INVALID, "ni_step: out_sample_stride < per_sample");
         if (d->x_next == d->x_in || d->x_next == d->out0 || d->x_next == d->out1 || (d->x0_dst != nullptr && d->x0_dst == d->x_next))
             return fail(NI_ERR_INVALID, "ni_step: x_next aliases an input or x0_dst");
@@ -849,10 +855,10 @@ int ni_step(const NiStepDesc *d, void *stream)
     a.per_sample = d->per_sample;
     a.out_sample_stride = d->has_x0 ? d->out_sample_stride : d->per_sample;
     a.out_strided = d->has_x0 && d->out_sample_stride != d->per_sample;
-    a.x_in = (d->has_x0 && d->a != 0.f) ? d->x_in : nullptr;
+    a.x_in = (d->has_x0 && (d->a != 0.f || d->c_xin != 0.f)) ? d->x_in : nullptr;
     a.out0 = d->out0; a.out1 = d->out1;
     a.x0_dst = d->x0_dst; a.x_next = d->x_next; a.x_next_lp = d->x_next_lp; a.sumsq = d->sumsq;
-    a.a = d->a; a.b0 = d->b0; a.b1 = d->b1; a.c_x0 = d->c_x0;
+    a.a = d->a; a.b0 = d->b0; a.b1 = d->b1; a.c_x0 = d->c_x0; a.c_xin = d->has_x0 ? d->c_xin : 0.f;
     a.k0 = (uint32_t)d->philox_seed; a.k1 = (uint32_t)(d->philox_seed >> 32);
     a.elem_offset = d->elem_offset;
     a.n_terms = d->n_terms; a.n_gen = d->n_gen;

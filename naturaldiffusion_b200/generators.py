@@ -71,18 +71,7 @@ def flow_euler_triple(num_step: int, sigmas=None) -> CoeffTriple:
 
 
 def markov_ratio(triple: CoeffTriple, tol: float = 1e-12):
-    """If rows satisfy row_k[:k] = c_k row_{k-1}[:k] (first-order samplers) return the c_k, else None.
-    Such matrices admit an O(1)-reads-per-step running update (hard part 2)."""
-    A, B, K = triple.A, triple.B, triple.K
-    cs = [0.0]
-    for k in range(1, K):
-        prev = np.concatenate([A[k - 1, :k], B[k - 1, : k + 1]])
-        cur = np.concatenate([A[k, :k], B[k, : k + 1]])
-        nz = np.abs(prev) > 0
-        if not nz.any():
-            return None
-        c = float(np.median(cur[nz] / prev[nz]))
-        if np.abs(cur - c * prev).max() > tol * max(1.0, np.abs(cur).max()):
-            return None
-        cs.append(c)
-    return np.array(cs)
+    """see coeffs.markov_ratios (kept here for discoverability next to the generators)"""
+    from .coeffs import markov_ratios
+    mr = markov_ratios(triple, tol)
+    return None if mr is None else np.array(mr[0])

@@ -92,7 +92,7 @@ class StepLaunch:
     __slots__ = ("desc", "_ptrs", "_coeffs", "_keep")
 
     def __init__(self, *, numel, per_sample, dtype, out_dtype=None, has_x0=True, x_in=0, out0=0, out1=0,
-                 out_sample_stride=None, a=0.0, b0=0.0, b1=0.0, x0_dst=0, c_x0=0.0,
+                 out_sample_stride=None, a=0.0, b0=0.0, b1=0.0, x0_dst=0, c_x0=0.0, c_xin=0.0,
                  terms=(), gens=(), seed=0, elem_offset=0, accumulate=False, x_next=0, x_next_lp=0, lp_dtype=NI_BF16, sumsq=0):
         """terms: iterable of (device_ptr, coeff); gens: iterable of (tensor_id, coeff, dst_ptr_or_0)."""
         terms = list(terms)
@@ -111,6 +111,7 @@ class StepLaunch:
         d.a, d.b0, d.b1 = float(a), float(b0), float(b1)
         d.x0_dst = x0_dst or None
         d.c_x0 = float(c_x0)
+        d.c_xin = float(c_xin)
         n = len(terms)
         self._ptrs = (C.c_void_p * max(n, 1))(*[p for p, _ in terms])
         self._coeffs = (C.c_float * max(n, 1))(*[float(c) for _, c in terms])
@@ -142,7 +143,7 @@ class StepLaunch:
 
 
 def fused_step(*, x_in: Optional[torch.Tensor], outs: Sequence[torch.Tensor], a: float, b: Sequence[float],
-               c_x0: float, terms: Sequence[tuple], gens: Sequence[tuple] = (), seed: int = 0, elem_offset: int = 0,
+               c_x0: float, terms: Sequence[tuple], gens: Sequence[tuple] = (), c_xin: float = 0.0, seed: int = 0, elem_offset: int = 0,
                per_sample: Optional[int] = None, out_sample_stride: Optional[int] = None, keep_x0: bool = True,
                keep_gen: Sequence[bool] = (), lp_dtype: Optional[torch.dtype] = None, want_sumsq: bool = False,
                state_dtype: Optional[torch.dtype] = None, shape=None, device=None):
@@ -181,7 +182,7 @@ def fused_step(*, x_in: Optional[torch.Tensor], outs: Sequence[torch.Tensor], a:
                    has_x0=has_x0, x_in=x_in.data_ptr() if x_in is not None else 0,
                    out0=outs[0].data_ptr() if has_x0 else 0, out1=outs[1].data_ptr() if len(outs) > 1 else 0,
                    out_sample_stride=out_sample_stride, a=a, b0=bb[0], b1=bb[1], x0_dst=x0.data_ptr() if x0 is not None else 0,
-                   c_x0=c_x0, terms=[(t.data_ptr(), c) for c, t in terms],
+                   c_x0=c_x0, c_xin=c_xin, terms=[(t.data_ptr(), c) for c, t in terms],
                    gens=[(tid, c, gen_dst[i].data_ptr() if gen_dst[i] is not None else 0) for i, (c, tid) in enumerate(gens)],
                    seed=seed, elem_offset=elem_offset, x_next=x_next.data_ptr(), x_next_lp=lp.data_ptr() if lp is not None else 0,
                    lp_dtype=_code(lp_dtype) if lp_dtype is not None else NI_BF16, sumsq=sumsq.data_ptr() if sumsq is not None else 0)

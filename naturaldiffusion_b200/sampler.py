@@ -32,7 +32,7 @@ class NaturalInferenceSampler:
     def __init__(self, triple: CoeffTriple, io_scaling: Sequence[Tuple[float, float, float]], batch: int,
                  sample_shape: Sequence[int], *, device="cuda", dtype: torch.dtype = torch.float32, seed: int = 0,
                  eps0: str = "stored", lp_dtype: Optional[torch.dtype] = None, track_sumsq: bool = False,
-                 sample_offset: int = 0, keep_all_x0: bool = False):
+                 sample_offset: int = 0, keep_all_x0: bool = False, markov="auto"):
         """
         triple       coefficient matrices (A, B, node)
         io_scaling   K tuples (a_k, b0_k, b1_k): x0_k = a_k x_k + b0_k out0 + b1_k out1 (coeffs.io_*)
@@ -41,6 +41,11 @@ class NaturalInferenceSampler:
         eps0         "stored": the initial noise lives in a slot and is re-read by every row that uses it
                      "regen" : rows regenerate it in-kernel from (seed, tensor 0) -- no slot, no reads
         lp_dtype     also emit x_{k+1} in fp16/bf16 for a reduced-precision denoiser (fp32 state only)
+        markov       "auto" | True | False.  First-order matrices (DDPM, DDIM, Euler, flow Euler; detected by
+                     coeffs.markov_ratios to 1e-12) satisfy row_k = c_k*row_{k-1} + new terms, so the history sum
+                     equals c_k*x_k and a step reads nothing but the model output and x_k: O(1) instead of O(k)
+                     transfers per step, no ring at all.  Same trajectory as the dense rows up to fp32 rounding
+                     (it is the original sampler's own arithmetic).
         """
         if eps0 not in ("stored", "regen"):
             raise NiError("eps0 must be 'stored' or 'regen'")
@@ -64,7 +69,9 @@ class NaturalInferenceSampler:
         self.eps0_mode = eps0
         self.lp_dtype = lp_dtype
         self.elem_offset = int(sample_offset) * self.per_sample
-        self.plan: StepPlan = build_plan(triple, keep_all_x0=keep_all_x0)
+        from .coeffs import markov_ratios
+        use_markov = (markov_ratios(triple) is not None) if markov == "auto" else bool(markov)
+        self.plan: StepPlan = build_plan(triple, keep_all_x0=keep_all_x0, markov=use_markov)
         p = self.plan
         # one slab: X ping-pong (2) + eps0 (1) + x0 ring + eps ring
         n_buf = 3 + p.n_x0_slots + p.n_eps_slots
@@ -132,6 +139,7 @@ class NaturalInferenceSampler:
                 row.append(StepLaunch(
                     **common, has_x0=ci == 0, x_in=x_in if ci == 0 else 0, a=a, b0=b0, b1=b1,
                     x0_dst=(self._x0_slots[s.x0_slot].data_ptr() if (s.keep_x0 and ci == 0) else 0), c_x0=s.c_x0,
+                    c_xin=s.c_xin if ci == 0 else 0.0,
                     terms=chunk, gens=gens if ci == 0 else (), accumulate=ci > 0, x_next=x_next,
                     x_next_lp=(self._lp[(k + 1) % 2].data_ptr() if (self._lp is not None and last) else 0),
                     lp_dtype=DTYPE_CODE[self.lp_dtype] if self.lp_dtype else NI_BF16,

@@ -35,7 +35,7 @@ def rel_err(got, ref):
 def test_library_loaded_is_in_tree():
     from naturaldiffusion_b200 import _lib
     assert os.path.samefile(os.path.dirname(_lib.LIB_PATH), os.path.dirname(_lib.__file__))
-    assert ni.lib().ni_version() == 1
+    assert ni.lib().ni_version() == 2
 
 
 @pytest.mark.parametrize("numel,off", [(4096, 0), (4100, 0), (1000, 4), (1001, 7), (5, 1), (1 << 20, 1 << 33)])
@@ -220,8 +220,9 @@ def test_cifar_loop_matches_reference_golden(golden_dir, weights_dir, name):
     assert torch.equal(s2.sample(den, noise=noise), x)
 
 
+@pytest.mark.parametrize("markov", [False, True])
 @pytest.mark.parametrize("alg,K", [("ddpm", 24), ("ddim", 24), ("ddpm_sympy", 18), ("ddim", 100)])
-def test_validate_loop_matches_reference_golden(golden_dir, alg, K):
+def test_validate_loop_matches_reference_golden(golden_dir, alg, K, markov):
     g = _g(golden_dir, "validate_loop.npz")
     m = _g(golden_dir, "reference_matrices.npz")
     fam, key = alg.replace("_sympy", ""), f"{alg}_{K:03d}"
@@ -235,10 +236,13 @@ def test_validate_loop_matches_reference_golden(golden_dir, alg, K):
         ts = torch.ones(z.shape[0], dtype=torch.int32, device=DEV) * int(triple.node[k, 0])
         return net(z, ts, 0), net(z, ts, 1)
 
-    s = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, 4.0), noise.shape[0], noise.shape[1:], device=DEV, keep_all_x0=True)
+    s = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, 4.0), noise.shape[0], noise.shape[1:], device=DEV, keep_all_x0=True, markov=markov)
+    assert s.plan.markov == markov and (s.plan.n_eps_slots == 0 if markov else True)
     z, trace = s.sample(den, noise=noise, fresh_noise=fresh, record=True)
+    # dense rows: the reference NI arithmetic; Markov rows (c_k * x_k stands for the history): the original sampler's
+    # arithmetic -- both within the reference's own NI-vs-original gap of the golden vectors
     for k in range(K):
-        assert rel_err(trace[k]["x_next"], torch.from_numpy(g[key + "/ni_x_next"][k])) < 1e-6, f"step {k}"
+        assert rel_err(trace[k]["x_next"], torch.from_numpy(g[key + "/ni_x_next"][k])) < (5e-6 if markov else 1e-6), f"step {k}"
     assert rel_err(z, torch.from_numpy(g[key + "/original_final"])) < 5e-6  # == the ORIGINAL ddpm/ddim sampler
 
 
@@ -253,8 +257,12 @@ def test_sd3_loop_matches_reference_golden(golden_dir, weights_dir, wname, tag, 
     net = ToyEps(16, seed=5)
     noise = torch.from_numpy(g[f"{wname}/{tag}/noise"]).to(DEV, dt)
     den = lambda x, k: (net(x, 1000 * float(sig[k]), 0), net(x, 1000 * float(sig[k]), 1))
-    s = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), noise.shape[0], noise.shape[1:], device=DEV, dtype=dt, keep_all_x0=True)
+    s = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), noise.shape[0], noise.shape[1:], device=DEV, dtype=dt, keep_all_x0=True, markov=False)
     out, trace = s.sample(den, noise=noise, record=True)
+    if wname == "sd3_step_28_weight":  # the default table is first-order in x0: x_k + eps_0 replace the 27-term history
+        sm = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), noise.shape[0], noise.shape[1:], device=DEV, dtype=dt)
+        assert sm.plan.markov and sm.plan.n_x0_slots == 0
+        assert rel_err(sm.sample(den, noise=noise), torch.from_numpy(g[f"{wname}/{tag}/out"][27])) < (5e-6 if dt == torch.float32 else 4e-3)
     for k in range(27):
         assert rel_err(trace[k]["x_next"], torch.from_numpy(g[f"{wname}/{tag}/x_in"][k + 1])) < tol, f"step {k}"
     assert rel_err(out, torch.from_numpy(g[f"{wname}/{tag}/out"][27])) < tol
@@ -359,9 +367,13 @@ def test_full_size_c4_ddpm250_equals_original_sampler():
     c1, c2, _ = ddim_x0_coeffs(K)
     net = ToyVPDenoiser(4, out_channels=8)
     den = lambda z, k: (net(z, triple.node[k, 0], 0), net(z, triple.node[k, 0], 1))
-    s = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, 4.0), B, (4, 32, 32), device=DEV, seed=0)
+    s = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, 4.0), B, (4, 32, 32), device=DEV, seed=0, markov=False)
     assert s.plan.n_x0_slots >= K - 2 and s.plan.n_eps_slots >= K - 2  # dense rows: everything stays live
-    z = s.sample(den)
+    z = s.sample(den).clone()
+    del s
+    sm = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, 4.0), B, (4, 32, 32), device=DEV, seed=0)  # markov="auto"
+    assert sm.plan.markov and sm.plan.n_x0_slots == 0 and sm.plan.n_eps_slots == 0 and sm.plan.total_units(2) == 4 * K
+    zm = sm.sample(den).clone()
     noise = philox_normal((B, 4, 32, 32), seed=0, tensor_id=0, device=DEV)
     fresh = [philox_normal((B, 4, 32, 32), seed=0, tensor_id=k + 1, device=DEV) for k in range(K)]
     eps_model = lambda zz, t: tuple(o[:, :4] for o in (net(zz, t, 0), net(zz, t, 1)))
@@ -370,6 +382,7 @@ def test_full_size_c4_ddpm250_equals_original_sampler():
     assert float(zo.abs().max()) < 50  # the trajectory is well-conditioned
     assert rel_err(z, zn) < 2e-6
     assert rel_err(zn, zo) < 1e-5 and rel_err(z, zo) < 1e-5
+    assert rel_err(zm, zo) < 2e-6 and rel_err(zm, zn) < 1e-5  # the O(1)-reads path IS the original sampler's arithmetic
 
 
 # ------------------------------------------------------------------ real (random-init) denoisers end to end

@@ -170,6 +170,35 @@ def test_generators_match_reference_matrices(golden_dir):
     assert generators.markov_ratio(m42) is None  # higher-order solvers are not Markov in the rows
 
 
+def test_markov_structure_detection_and_identity(weights_dir):
+    """first-order x0 structure: row_k . history == c_k * x_k + R_k . eps, for every family that has it"""
+    from naturaldiffusion_b200.coeffs import markov_ratios
+    fams = {"ddpm24": generators.ddpm_triple(24), "ddim100": generators.ddim_triple(100), "flow18": generators.flow_euler_triple(18),
+            "sd3": CoeffTriple.from_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight.csv"))}
+    for name, t in fams.items():
+        cs, R = markov_ratios(t)
+        K = t.K
+        prev = np.zeros(2 * K + 1)
+        prev[K] = 1.0  # x_0 = eps_0
+        for k in range(K):
+            row = np.concatenate([t.A[k], t.B[k]])
+            rec = cs[k] * prev
+            rec[k] = t.A[k, k]
+            rec[K:K + k + 1] += R[k, :k + 1]
+            rec[K + k + 1] = t.B[k, k + 1]
+            assert np.abs(rec - row).max() < 1e-11, (name, k)
+            prev = row
+        p = build_plan(t, markov=True)
+        assert p.markov and p.n_x0_slots == 0
+        assert (R != 0).sum() == (27 if name == "sd3" else 0)  # only the 2-decimal SD3 table needs an eps_0 correction
+        assert p.total_units(2) == sum(2 + 1 + 1 + len(s.eps) for s in p.steps)
+    for name in ("step_10_weight_42", "step_15_weight_173"):
+        assert markov_ratios(CoeffTriple.from_npz(os.path.join(weights_dir, name + ".npz"))) is None
+    assert markov_ratios(CoeffTriple.from_sd3_csv(os.path.join(weights_dir, "sd3_step_28_weight_sharp.csv"))) is None
+    with pytest.raises(ValueError):
+        build_plan(CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz")), markov=True)
+
+
 def test_schedule_helpers():
     assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
     assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
