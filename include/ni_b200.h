@@ -104,7 +104,8 @@ const char *ni_last_error(void);
 int64_t ni_launch_count(void);
 
 /* Tuning knobs, process-wide: "variant" 0 auto | 1 direct-load kernel | 2 TMA-staged kernel when eligible;
- * "tma_max_stages" 2..32; "tma_warps" 1..16; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4.  Results do not depend on them. */
+ * "tma_max_stages" 2..32; "tma_warps" 1..16; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4; "pdl" 0|1 (programmatic
+ * dependent launch of the direct-load step kernel, default 1).  Results do not depend on them. */
 int ni_set_option(const char *name, int value);
 
 int ni_step(const NiStepDesc *desc_host, void *stream);

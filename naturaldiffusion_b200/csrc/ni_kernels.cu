@@ -52,6 +52,7 @@ std::atomic<int> g_tma_max_stages{32};
 std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
 std::atomic<int> g_tma_ctas_per_sm{1};
+std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernel
 
 int fail(int code, const char *fmt, ...)
 {
@@ -386,9 +387,12 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int6
 template <typename T, typename TO, int VEC, int CAP>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
+    // PDL: let the next grid start launching now; do not touch global memory before the previous grid is complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
     if (v >= s.nvec) return;
     const int64_t e = v * VEC; // first element of this thread
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // issue the x0-stage loads (consumed after the term loop)
     Raw<T, VEC> rx;
@@ -715,6 +719,25 @@ int check_launch(const char *what)
     return NI_OK;
 }
 
+// Launch with programmatic dependent launch (PDL): the kernel calls griddepcontrol.launch_dependents at its top and
+// griddepcontrol.wait before its first global access, so the next ni_step's CTAs are already resident and parked
+// when this grid drains -- back-to-back steps (CUDA-graph replay, small tensors) lose no launch bubble.  After a
+// kernel that never triggers (a torch denoiser kernel) it degrades to ordinary stream order.
+template <typename Kern, typename... Args> void launch_pdl(Kern kern, unsigned blocks, cudaStream_t st, const Args &...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(NI_BLOCK);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl.load() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename T, typename TO, int VEC>
 int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
 {
@@ -723,11 +746,11 @@ int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
         TermTable<32> tab;
         memset(&tab, 0, sizeof(tab));
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        ni_step_kernel<T, TO, VEC, 32><<<blocks, NI_BLOCK, 0, st>>>(a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, 32>, blocks, st, a, tab);
     } else {
         static thread_local TermTable<NI_MAX_TERMS> tab;
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        ni_step_kernel<T, TO, VEC, NI_MAX_TERMS><<<blocks, NI_BLOCK, 0, st>>>(a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, NI_MAX_TERMS>, blocks, st, a, tab);
     }
     return check_launch("ni_step launch");
 }
@@ -817,6 +840,7 @@ int ni_set_option(const char *name, int value)
     if (!strcmp(name, "tma_max_stages")) { if (value < 2 || value > TMA_MAX_STAGES) return fail(NI_ERR_INVALID, "tma_max_stages must be 2..%d", TMA_MAX_STAGES); g_tma_max_stages = value; return NI_OK; }
     if (!strcmp(name, "tma_warps")) { if (value < 1 || value > TMA_MAX_WARPS) return fail(NI_ERR_INVALID, "tma_warps must be 1..%d", TMA_MAX_WARPS); g_tma_warps = value; return NI_OK; }
     if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
+    if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NI_OK; }
     if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
     return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);
 }

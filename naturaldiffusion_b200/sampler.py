@@ -84,6 +84,7 @@ class NaturalInferenceSampler:
         self.sumsq = torch.zeros((self.K, self.batch), dtype=torch.float32, device=self.device) if track_sumsq else None
         self._launches: Optional[List[List[StepLaunch]]] = None
         self._launch_key = None
+        self._launch_cache = {}
         self._graph = None
         self._graph_out = None
         self.kernel_launches_per_trajectory = sum(p.launches(k, eps0 == "stored") for k in range(self.K))
@@ -103,6 +104,9 @@ class NaturalInferenceSampler:
     def _prepare(self, x_init_ptr: int, eps0_ptr: int, fresh_ptrs: Optional[Sequence[int]], out_ptr: int, stored0: bool):
         key = (x_init_ptr, eps0_ptr, tuple(fresh_ptrs) if fresh_ptrs is not None else None, out_ptr, stored0)
         if self._launches is not None and key == self._launch_key:
+            return
+        if key in self._launch_cache:  # e.g. the two alternating staging buffers of sample_host_many
+            self._launches, self._launch_key = self._launch_cache[key], key
             return
         p, code = self.plan, DTYPE_CODE[self.dtype]
         launches: List[List[StepLaunch]] = []
@@ -145,6 +149,9 @@ class NaturalInferenceSampler:
                     lp_dtype=DTYPE_CODE[self.lp_dtype] if self.lp_dtype else NI_BF16,
                     sumsq=(self.sumsq[k].data_ptr() if (self.sumsq is not None and last) else 0)))
             launches.append(row)
+        if len(self._launch_cache) >= 8:
+            self._launch_cache.pop(next(iter(self._launch_cache)))
+        self._launch_cache[key] = launches
         self._launches, self._launch_key = launches, key
 
     def _check_out(self, o: torch.Tensor, k: int):
@@ -269,6 +276,59 @@ class NaturalInferenceSampler:
             x = to_pixel_u8(x, out=self._pix)
         out_host.copy_(x, non_blocking=True)
         return out_host
+
+
+    @torch.no_grad()
+    def sample_host_many(self, denoiser: Callable, noise_hosts: Sequence[torch.Tensor], out_hosts: Sequence[torch.Tensor], pixels: bool = False):
+        """Pipelined end-to-end over many batches with HOST buffers (the reference generates 100 batches of 500,
+        src/CIFAR10NaturalInference.py:288-309): the H2D copy of batch i+1 and the D2H copy of batch i-1 run on
+        their own streams while batch i computes; two device staging buffers per direction.  Returns after
+        enqueueing everything; the caller synchronises (torch.cuda.synchronize or the returned event)."""
+        n = len(noise_hosts)
+        if len(out_hosts) != n:
+            raise NiError("need one output buffer per noise batch")
+        shape = self.full_shape()
+        dev = self.device
+        if not hasattr(self, "_stage"):
+            b, (c, h, w) = self.batch, self.sample_shape
+            self._stage = dict(
+                noise=[torch.empty(shape, dtype=self.dtype, device=dev) for _ in range(2)],
+                out=[(torch.empty((b, h, w, c), dtype=torch.uint8, device=dev) if pixels else torch.empty(shape, dtype=self.dtype, device=dev)) for _ in range(2)],
+                pixels=pixels, h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev))
+        st = self._stage
+        if st["pixels"] != pixels:
+            raise NiError("sample_host_many was first used with a different `pixels` setting on this sampler")
+        main = torch.cuda.current_stream(dev)
+        c_done, d_done = [None] * n, [None] * n
+        for i in range(n):
+            nh = noise_hosts[i]
+            if nh.device.type != "cpu" or nh.shape != shape or nh.dtype != self.dtype:
+                raise NiError("noise_hosts[i] must be CPU tensors matching the state shape/dtype")
+            nb, ob = st["noise"][i % 2], st["out"][i % 2]
+            with torch.cuda.stream(st["h2d"]):
+                if i >= 2:
+                    st["h2d"].wait_event(c_done[i - 2])      # batch i-2 no longer reads this noise buffer
+                else:
+                    st["h2d"].wait_stream(main)
+                nb.copy_(nh, non_blocking=True)
+                h_done = torch.cuda.Event()
+                h_done.record(st["h2d"])
+            main.wait_event(h_done)
+            if i >= 2:
+                main.wait_event(d_done[i - 2])                # batch i-2's result has left this output buffer
+            if pixels:
+                to_pixel_u8(self.sample(denoiser, noise=nb), out=ob)
+            else:
+                self.sample(denoiser, noise=nb, out=ob)
+            c_done[i] = torch.cuda.Event()
+            c_done[i].record(main)
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(c_done[i])
+                out_hosts[i].copy_(ob, non_blocking=True)
+                d_done[i] = torch.cuda.Event()
+                d_done[i].record(st["d2h"])
+        main.wait_stream(st["d2h"])
+        return d_done[-1] if n else None
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -23,6 +23,8 @@ RUNS = [
     ("c3", ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=2"]),
 ]
 libs = [a for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--lib"] or [None]
+if "--pdl" in sys.argv:
+    RUNS = [(c, ["--opt", f"pdl={v}"] + e) for c, e in (("c2", []), ("c3", []), ("c4", []), ("c5", []), ("c5", ["--batch", "4"])) for v in (0, 1)]
 if "--ldg-only" in sys.argv:
     RUNS = [("c2", ["--variant", "1"]), ("c3", ["--variant", "1"])]
 out = []
@@ -31,7 +33,7 @@ for lib in libs:
         env = dict(os.environ)
         if lib:
             env["NI_B200_LIB"] = os.path.abspath(lib)
-        steps = "1500" if cfg == "c2" else "300"
+        steps = {"c2": "1500", "c3": "300", "c4": "50", "c5": "300"}.get(cfg, "100")
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", cfg, "--steps", steps, "--warmup", "20", "--no-cpu-baseline", "--no-e2e"] + extra
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         try:

@@ -336,6 +336,31 @@ def test_full_size_c2_sharding_and_regen_bit_identical(weights_dir):
     assert torch.equal(torch.cat(halves), ref)
 
 
+def test_host_buffer_paths_match_device_path(weights_dir):
+    """end-to-end entry points with HOST buffers (single call and the double-buffered pipeline over many batches)
+    return exactly what the device-resident path computes, including the fused uint8 output stage"""
+    den = lambda x, k: torch.tanh(0.7 * x) * (1.0 + 0.01 * k) + 0.1 * x
+    triple, s = _c2_sampler(weights_dir, 256)
+    g = torch.Generator().manual_seed(4)
+    noises = [torch.randn(256, 3, 32, 32, generator=g).pin_memory() for _ in range(5)]
+    outs = [torch.empty(256, 32, 32, 3, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    s.sample_host_many(den, noises, outs, pixels=True)
+    torch.cuda.synchronize()
+    refs = [to_pixel_u8(s.sample(den, noise=n.to(DEV))).cpu() for n in noises]
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    o1 = torch.empty(256, 32, 32, 3, dtype=torch.uint8).pin_memory()
+    s.sample_host(den, noises[3], o1, pixels=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, refs[3])
+    _, s2 = _c2_sampler(weights_dir, 256)
+    lat = [torch.empty(256, 3, 32, 32).pin_memory() for _ in range(3)]
+    s2.sample_host_many(den, noises[:3], lat, pixels=False)
+    torch.cuda.synchronize()
+    for n, o in zip(noises, lat):
+        assert torch.equal(o, s2.sample(den, noise=n.to(DEV)).cpu())
+
+
 def test_full_size_c2_linearity(weights_dir):
     """with a linear denoiser the whole trajectory is linear in the initial noise"""
     den = lambda x, k: (0.3 + 0.01 * k) * x
