@@ -75,3 +75,145 @@ def markov_ratio(triple: CoeffTriple, tol: float = 1e-12):
     from .coeffs import markov_ratios
     mr = markov_ratios(triple, tol)
     return None if mr is None else np.array(mr[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# any linear sampler -> matrices, by running it in coefficient space
+# ----------------------------------------------------------------------------------------------
+
+class VPLinearSchedule:
+    """Continuous VP schedule beta(t) = beta_0 + t (beta_1 - beta_0): log alpha, alpha, sigma, lambda = log(alpha/sigma)
+    and its inverse (the `NoiseScheduleVP('linear')` of deps/dpm_solver_pytorch.py:6-167, float64 numpy)."""
+
+    def __init__(self, beta_0=0.1, beta_1=20.0):
+        self.b0, self.b1 = beta_0, beta_1
+
+    def log_alpha(self, t):
+        return -0.25 * t ** 2 * (self.b1 - self.b0) - 0.5 * t * self.b0
+
+    def alpha(self, t):
+        return np.exp(self.log_alpha(t))
+
+    def sigma(self, t):
+        return np.sqrt(1.0 - np.exp(2.0 * self.log_alpha(t)))
+
+    def lam(self, t):
+        la = self.log_alpha(t)
+        return la - 0.5 * np.log(1.0 - np.exp(2.0 * la))
+
+    def inv_lam(self, lam):
+        tmp = 2.0 * (self.b1 - self.b0) * np.logaddexp(-2.0 * lam, 0.0)
+        return tmp / (np.sqrt(self.b0 ** 2 + tmp) + self.b0) / (self.b1 - self.b0)
+
+
+class CoefficientTracer:
+    """Run an (unmodified, linear) sampler on vectors of R^{2K+1} over the basis (y_0..y_{K-1}, eps_0..eps_K):
+    `model(x, t)` hands back the unit vector of the next x0-prediction and records x as a matrix row -- the state a
+    sampler feeds to its j-th model call IS row j-1 of [A|B] -- `noise()` hands back the next noise unit vector.
+    What the reference does with sympy symbols (src/AnalyzeDPMSolver.py:272-281, src/AnalyzeDEIS.py:80-87), done with
+    plain linear algebra."""
+
+    def __init__(self, num_calls: int, schedule=None):
+        self.K, self.ns = num_calls, schedule
+        self.rows, self.nodes, self.calls, self.draws = [], [], 0, 0
+
+    def unit(self, i):
+        v = np.zeros(2 * self.K + 1)
+        v[i] = 1.0
+        return v
+
+    def noise(self):
+        v = self.unit(self.K + self.draws)
+        self.draws += 1
+        return v
+
+    def _node(self, t):
+        self.nodes.append([t, self.ns.alpha(t), self.ns.sigma(t)] if self.ns is not None else [t, np.nan, np.nan])
+
+    def model_x0(self, x, t):
+        """data-prediction call"""
+        if self.calls > 0:
+            self.rows.append(np.array(x, dtype=np.float64))
+        self._node(t)
+        self.calls += 1
+        return self.unit(self.calls - 1)
+
+    def model_eps(self, x, t):
+        """noise-prediction call: eps = (x - alpha y)/sigma with y the new x0 symbol"""
+        y = self.model_x0(x, t)
+        return (np.asarray(x) - self.ns.alpha(t) * y) / self.ns.sigma(t)
+
+    def finish(self, x, t, name="") -> CoeffTriple:
+        self.rows.append(np.array(x, dtype=np.float64))
+        self._node(t)
+        if self.calls != self.K or len(self.rows) != self.K:
+            raise ValueError(f"sampler made {self.calls} model calls, expected {self.K}")
+        M = np.stack(self.rows)
+        A, B = M[:, : self.K], M[:, self.K:]
+        # columns of noise never drawn stay zero; lower-triangular structure is checked by CoeffTriple
+        return CoeffTriple(A, B, np.array(self.nodes), name=name)
+
+
+def quadratic_time_grid(K: int, t_T=1.0, t_0=1e-3):
+    """`time_quadratic` spacing (deps/dpm_solver_pytorch.py:475-478): the grid of weights/step_*_weight_*.npz"""
+    return np.linspace(t_T ** 0.5, t_0 ** 0.5, K + 1) ** 2
+
+
+def dpm_solver_pp_2s_triple(steps: int, t_T=1.0, t_0=1e-3, r1=0.5) -> CoeffTriple:
+    """Singlestep DPM-Solver++(2S) on a uniform time grid, 2 model calls per step -> K = 2*steps rows
+    (what src/AnalyzeDPMSolver.py:329-425 derives with sympy; update of deps/dpm_solver_pytorch.py:594-676)."""
+    ns = VPLinearSchedule()
+    ts = np.linspace(t_T, t_0, steps + 1)
+    tr = CoefficientTracer(2 * steps, ns)
+    x = tr.noise()
+    for i in range(steps):
+        s, t = ts[i], ts[i + 1]
+        h = ns.lam(t) - ns.lam(s)
+        s1 = ns.inv_lam(ns.lam(s) + r1 * h)
+        y_s = tr.model_x0(x, s)
+        x_s1 = ns.sigma(s1) / ns.sigma(s) * x - ns.alpha(s1) * np.expm1(-r1 * h) * y_s
+        y_s1 = tr.model_x0(x_s1, s1)
+        phi = ns.alpha(t) * np.expm1(-h)
+        x = ns.sigma(t) / ns.sigma(s) * x - phi * y_s - (0.5 / r1) * phi * (y_s1 - y_s)
+    return tr.finish(x, ts[-1], name=f"dpmsolverpp2s_{2 * steps:03d}")
+
+
+def dpm_solver_2s_triple(steps: int, t_T=1.0, t_0=1e-3, r1=0.5) -> CoeffTriple:
+    """Singlestep DPM-Solver-2 (noise prediction) on a uniform time grid (src/AnalyzeDPMSolver.py:228-326)."""
+    ns = VPLinearSchedule()
+    ts = np.linspace(t_T, t_0, steps + 1)
+    tr = CoefficientTracer(2 * steps, ns)
+    x = tr.noise()
+    for i in range(steps):
+        s, t = ts[i], ts[i + 1]
+        h = ns.lam(t) - ns.lam(s)
+        s1 = ns.inv_lam(ns.lam(s) + r1 * h)
+        e_s = tr.model_eps(x, s)
+        x_s1 = np.exp(ns.log_alpha(s1) - ns.log_alpha(s)) * x - ns.sigma(s1) * np.expm1(r1 * h) * e_s
+        e_s1 = tr.model_eps(x_s1, s1)
+        phi = ns.sigma(t) * np.expm1(h)
+        x = np.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - phi * e_s - (0.5 / r1) * phi * (e_s1 - e_s)
+    return tr.finish(x, ts[-1], name=f"dpmsolver2s_{2 * steps:03d}")
+
+
+def dpm_solver_pp_2m_triple(K: int, grid="time_quadratic", t_T=1.0, t_0=1e-3) -> CoeffTriple:
+    """Multistep DPM-Solver++(2M), one model call per step: first step first-order
+    (deps/dpm_solver_pytorch.py:547-576), then the second-order multistep update (:796-831).  With the quadratic
+    grid this is the sampler BASELINE config 3 names; the shipped step_15_weight_173 is a hand-tuned banded matrix on
+    the same grid, this is the true solver's (dense) matrix."""
+    ns = VPLinearSchedule()
+    ts = quadratic_time_grid(K, t_T, t_0) if grid == "time_quadratic" else np.linspace(t_T, t_0, K + 1)
+    tr = CoefficientTracer(K, ns)
+    x = tr.noise()
+    prev_y, prev_t = None, None
+    for i in range(K):
+        s, t = ts[i], ts[i + 1]
+        y = tr.model_x0(x, s)
+        h = ns.lam(t) - ns.lam(s)
+        phi = ns.alpha(t) * np.expm1(-h)
+        nxt = ns.sigma(t) / ns.sigma(s) * x - phi * y
+        if prev_y is not None:
+            r0 = (ns.lam(s) - ns.lam(prev_t)) / h
+            nxt = nxt - 0.5 * phi * (1.0 / r0) * (y - prev_y)
+        prev_y, prev_t, x = y, s, nxt
+    return tr.finish(x, ts[-1], name=f"dpmsolverpp2m_{K:03d}")

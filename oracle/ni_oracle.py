@@ -421,3 +421,41 @@ def npz_bytes(**arrays):
     buf = io.BytesIO()
     np.savez(buf, **arrays)
     return buf.getvalue()
+
+
+# --------------------------------------------------------------------------------------
+# DPM-Solver++(2M), the original multistep sampler (comparator for generated matrices)
+# --------------------------------------------------------------------------------------
+
+
+def vp_linear(t, b0=0.1, b1=20.0):
+    """(log alpha, alpha, sigma, lambda) of the continuous VP schedule, as NoiseScheduleVP('linear') computes them
+    (deps/dpm_solver_pytorch.py:128-154), on fp32 torch scalars like the reference's solver."""
+    t = torch.as_tensor(t, dtype=torch.float32)
+    la = -0.25 * t**2 * (b1 - b0) - 0.5 * t * b0
+    sig = torch.sqrt(1.0 - torch.exp(2.0 * la))
+    return la, torch.exp(la), sig, la - torch.log(sig)
+
+
+@torch.no_grad()
+def dpmpp_2m_original_loop(ts, eps_model, noise):
+    """DPM_Solver(algorithm_type='dpmsolver++').sample(method='multistep', order=2, lower_order_final=False) on the
+    time grid `ts` (K+1 nodes): first step = dpm_solver_first_update (deps/dpm_solver_pytorch.py:547-576), then
+    multistep_dpm_solver_second_update (:796-831, solver_type 'dpmsolver'); the data-prediction model is
+    x0 = (x - sigma*eps)/alpha (:262-271 `data_prediction_fn` without thresholding)."""
+    x = noise.clone()
+    prev_m, prev_t = None, None
+    for i in range(len(ts) - 1):
+        s, t = float(ts[i]), float(ts[i + 1])
+        _, a_s, sg_s, lam_s = vp_linear(s)
+        _, a_t, sg_t, lam_t = vp_linear(t)
+        m = (x - sg_s * eps_model(x, s)) / a_s
+        h = lam_t - lam_s
+        phi = torch.expm1(-h)
+        nxt = (sg_t / sg_s) * x - (a_t * phi) * m
+        if prev_m is not None:
+            lam_p = vp_linear(prev_t)[3]
+            r0 = (lam_s - lam_p) / h
+            nxt = nxt - 0.5 * (a_t * phi) * ((1.0 / r0) * (m - prev_m))
+        prev_m, prev_t, x = m, s, nxt
+    return x

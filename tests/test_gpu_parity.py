@@ -474,3 +474,24 @@ def test_dit_and_mmdit_adapters_drive_the_sampler():
     n3 = philox_normal((2, 16, 32, 32), seed=10, tensor_id=0, dtype=torch.float16, device=DEV)
     ref, _ = O.sd3_ni_loop(W, sig, lambda x, k: mmdit_cfg_denoiser(mm, sig, ctx, pooled, nctx, npooled, batched=False)(x, k), n3.float())
     assert rel_err(out.float(), ref) < 3e-3  # fp16 state vs the loop evaluated in fp32 on an fp16 network
+
+
+def test_dpm_solver_pp_2m_matrix_equals_original_multistep_solver():
+    """BASELINE config 3's named sampler: DPM-Solver++(2M), 15 steps, quadratic time grid, CIFAR shapes.  Its matrix
+    is generated by the coefficient-space tracer (dense 15x15) and run through the fused step; the ORIGINAL multistep
+    solver (oracle restatement of deps/dpm_solver_pytorch.py:547-576,796-831) on the same noise gives the same samples."""
+    from naturaldiffusion_b200.generators import VPLinearSchedule, dpm_solver_pp_2m_triple
+    K, B = 15, 256
+    triple = dpm_solver_pp_2m_triple(K)
+    ns = VPLinearSchedule()
+    ts = triple.node[:, 0]
+    io = [(1.0 / ns.alpha(t), -ns.sigma(t) / ns.alpha(t), 0.0) for t in ts[:-1]]  # x0 = (x - sigma*eps)/alpha
+    net = ToyEps(3, seed=11, t_scale=0.3)
+    eps_model = lambda x, t: float(ns.sigma(t)) * x + 0.1 * net(x, float(t))  # bounded eps-predictor (see ToyVPDenoiser)
+    s = NaturalInferenceSampler(triple, io, B, (3, 32, 32), device=DEV, seed=5)
+    assert not s.plan.markov and s.plan.n_x0_slots == K - 1
+    x = s.sample(lambda z, k: eps_model(z, ts[k]))
+    noise = philox_normal((B, 3, 32, 32), seed=5, tensor_id=0, device=DEV)
+    xo = O.dpmpp_2m_original_loop(ts, eps_model, noise)
+    assert float(xo.abs().max()) < 50
+    assert rel_err(x, xo) < 1e-5

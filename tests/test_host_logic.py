@@ -199,6 +199,35 @@ def test_markov_structure_detection_and_identity(weights_dir):
         build_plan(CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz")), markov=True)
 
 
+def test_coefficient_space_tracer_reproduces_reference_dpm_solver_matrices(golden_dir, weights_dir):
+    """f2: running a linear sampler on coefficient-space vectors yields its matrix; DPM-Solver-2S and DPM-Solver++(2S)
+    reproduce the 8 matrices the reference derived with sympy (results/dpmsolver*/), and the multistep ++(2M) matrix on
+    the quadratic grid has the nodes of weights/step_15_weight_173 (BASELINE config 3)"""
+    m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
+    for fam, fn in (("dpmsolverpp/dpmsolverpp2s", generators.dpm_solver_pp_2s_triple), ("dpmsolver/dpmsolver2s", generators.dpm_solver_2s_triple)):
+        for K in (18, 24, 100, 200):
+            t = fn(K // 2)
+            key = f"{fam}_{K:03d}"
+            assert np.abs(t.A - m[key + "/A"]).max() < 1e-12 and np.abs(t.B - m[key + "/B"]).max() < 1e-12, key
+            assert np.abs(t.node - m[key + "/node"]).max() < 1e-12
+    t = generators.dpm_solver_pp_2m_triple(15)
+    ref = CoeffTriple.from_npz(os.path.join(weights_dir, "step_15_weight_173.npz"))
+    assert np.abs(t.node - ref.node).max() < 1e-6  # same quadratic grid / VP marginals (the file carries fp32 round-off)
+    assert np.abs(t.A.sum(1) - t.node[1:, 1]).max() < 7e-3 and np.count_nonzero(t.B[:, 1:]) == 0
+    assert build_plan(t).n_x0_slots == 15 - 1  # a true multistep solver is dense: every x0 stays live
+    from naturaldiffusion_b200.coeffs import markov_ratios
+    assert markov_ratios(t) is None
+    # the tracer on a first-order sampler gives the closed form
+    ns, ts = generators.VPLinearSchedule(), np.linspace(1.0, 1e-3, 11)
+    tr = generators.CoefficientTracer(10, ns)
+    x = tr.noise()
+    for i in range(10):
+        y = tr.model_x0(x, ts[i])
+        x = ns.sigma(ts[i + 1]) / ns.sigma(ts[i]) * x + (ns.alpha(ts[i + 1]) - ns.sigma(ts[i + 1]) / ns.sigma(ts[i]) * ns.alpha(ts[i])) * y  # DDIM
+    d = tr.finish(x, ts[-1])
+    assert markov_ratios(d) is not None and np.abs(d.A.sum(1) + d.B[:, 0] * 0 - d.node[1:, 1]).max() < 7e-3
+
+
 def test_schedule_helpers():
     assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
     assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
