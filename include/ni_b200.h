@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NI_ABI_VERSION 2
+#define NI_ABI_VERSION 3
 #define NI_MAX_TERMS 512 /* stored history/noise terms per launch; longer rows: call twice with accumulate */
 #define NI_MAX_GEN 4     /* noise terms generated in-kernel per launch */
 
@@ -92,10 +92,16 @@ typedef struct NiStepDesc {
     uint64_t elem_offset;      /* global index of this shard's element 0 */
 
     int32_t accumulate;        /* 1: x_next += (this launch) -- used to chain rows longer than NI_MAX_TERMS */
-    void *x_next;              /* x_{k+1}; must not alias any input */
+    float bias;                /* constant added to x_next (output stage of latent models: x/scaling_factor + shift_factor,
+                                  src/SD3NaturalInference.py:238; the 1/scaling_factor goes into the row coefficients) */
+    void *x_next;              /* x_{k+1}; must not alias any input.  May be NULL when pixels_u8 is given */
     void *x_next_lp;           /* optional copy of x_next in lp_dtype for a reduced-precision denoiser */
     int32_t lp_dtype;
     float *sumsq;              /* optional [batch_local] fp32: += sum over the sample of x_next^2 (caller zeroes) */
+    uint8_t *pixels_u8;        /* optional, last step: NHWC uint8 = trunc(clip((x_next*px_scale + px_shift)*255, 0, 255)), the
+                                  output stage of src/CIFAR10NaturalInference.py:308-309,212-216 fused into the step */
+    float px_scale, px_shift;
+    int32_t px_channels;       /* C of the NCHW sample (per_sample = C*H*W) */
 } NiStepDesc;
 
 int ni_version(void);

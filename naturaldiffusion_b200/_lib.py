@@ -13,7 +13,7 @@ import os
 NI_F32, NI_F16, NI_BF16, NI_F64 = 0, 1, 2, 3
 NI_MAX_TERMS = 512
 NI_MAX_GEN = 4
-NI_ABI_VERSION = 2
+NI_ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NI_B200_LIB", os.path.join(_HERE, "libni_b200.so"))
@@ -51,10 +51,15 @@ class NiStepDesc(C.Structure):
         ("philox_seed", C.c_uint64),
         ("elem_offset", C.c_uint64),
         ("accumulate", C.c_int32),
+        ("bias", C.c_float),
         ("x_next", C.c_void_p),
         ("x_next_lp", C.c_void_p),
         ("lp_dtype", C.c_int32),
         ("sumsq", C.c_void_p),
+        ("pixels_u8", C.c_void_p),
+        ("px_scale", C.c_float),
+        ("px_shift", C.c_float),
+        ("px_channels", C.c_int32),
     ]
 
 

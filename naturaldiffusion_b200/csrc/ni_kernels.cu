@@ -288,7 +288,9 @@ struct StepArgs {
     uint64_t gen_tid[NI_MAX_GEN];
     uint64_t elem_offset;
     float gen_c[NI_MAX_GEN];
-    float a, b0, b1, c_x0, c_xin;
+    float a, b0, b1, c_x0, c_xin, bias, px_scale, px_shift;
+    uint8_t *pixels;
+    int px_channels;
     uint32_t k0, k1;
     int n_terms, n_gen;
     int has_x0, out_strided, accumulate, lp_dtype;
@@ -352,8 +354,25 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int6
         }
     }
 
-    // x_{k+1}
-    store_raw<T, VEC>(static_cast<T *>(s.x_next) + e, pack<T, VEC>(acc));
+    // x_{k+1} (+ constant: the latent shift of the output stage, 0 otherwise)
+    if (s.bias != 0.f) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += s.bias;
+    }
+    if (s.x_next != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x_next) + e, pack<T, VEC>(acc));
+    // fused output stage of the LAST step: NCHW float -> NHWC uint8 with the reference's truncating cast.  The VEC
+    // elements of a thread are consecutive w of one channel, so they land C bytes apart.
+    if (s.pixels != nullptr) {
+        const int64_t n = e / s.per_sample, r = e - n * s.per_sample;
+        const int64_t hw_total = s.per_sample / s.px_channels;
+        const int64_t c = r / hw_total, hw = r - c * hw_total;
+        uint8_t *dst = s.pixels + (n * hw_total + hw) * s.px_channels + c;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float y = (round_to<T>(acc[i]) * s.px_scale + s.px_shift) * 255.0f;
+            dst[(int64_t)i * s.px_channels] = (uint8_t)(int)fminf(fmaxf(y, 0.f), 255.f);
+        }
+    }
     if (s.x_next_lp != nullptr) {
         if (s.lp_dtype == NI_BF16) store_raw<__nv_bfloat16, VEC>(static_cast<__nv_bfloat16 *>(s.x_next_lp) + e, pack<__nv_bfloat16, VEC>(acc));
         else store_raw<__half, VEC>(static_cast<__half *>(s.x_next_lp) + e, pack<__half, VEC>(acc));
@@ -852,18 +871,20 @@ int ni_step(const NiStepDesc *d, void *stream)
     if (d->numel % d->per_sample != 0) return fail(NI_ERR_INVALID, "ni_step: numel %lld is not a multiple of per_sample %lld", (long long)d->numel, (long long)d->per_sample);
     if (d->n_terms < 0 || d->n_terms > NI_MAX_TERMS) return fail(NI_ERR_TOO_MANY, "ni_step: n_terms=%d exceeds NI_MAX_TERMS=%d (chain launches with accumulate=1)", d->n_terms, NI_MAX_TERMS);
     if (d->n_gen < 0 || d->n_gen > NI_MAX_GEN) return fail(NI_ERR_TOO_MANY, "ni_step: n_gen=%d exceeds NI_MAX_GEN=%d", d->n_gen, NI_MAX_GEN);
-    if (d->x_next == nullptr) return fail(NI_ERR_INVALID, "ni_step: x_next is NULL");
+    if (d->x_next == nullptr && d->pixels_u8 == nullptr) return fail(NI_ERR_INVALID, "ni_step: x_next is NULL (allowed only with pixels_u8)");
+    if (d->pixels_u8 != nullptr && (d->px_channels <= 0 || d->per_sample % d->px_channels != 0)) return fail(NI_ERR_INVALID, "ni_step: pixels_u8 needs px_channels dividing per_sample");
+    if (d->x_next == nullptr && (d->accumulate || d->x_next_lp != nullptr || d->sumsq != nullptr)) return fail(NI_ERR_INVALID, "ni_step: accumulate / x_next_lp / sumsq need x_next");
     if (d->n_terms > 0 && (d->term_ptrs_host == nullptr || d->term_coeffs_host == nullptr)) return fail(NI_ERR_INVALID, "ni_step: term tables are NULL");
     if (d->has_x0) {
         if (d->out0 == nullptr) return fail(NI_ERR_INVALID, "ni_step: has_x0 but out0 is NULL");
         if (d->x_in == nullptr && (d->a != 0.f || d->c_xin != 0.f)) return fail(NI_ERR_INVALID, "ni_step: a or c_xin != 0 but x_in is NULL");
         if (d->out_sample_stride < d->per_sample) return fail(NI_ERR_INVALID, "ni_step: out_sample_stride < per_sample");
-        if (d->x_next == d->x_in || d->x_next == d->out0 || d->x_next == d->out1 || (d->x0_dst != nullptr && d->x0_dst == d->x_next))
+        if (d->x_next != nullptr && (d->x_next == d->x_in || d->x_next == d->out0 || d->x_next == d->out1 || d->x0_dst == d->x_next))
             return fail(NI_ERR_INVALID, "ni_step: x_next aliases an input or x0_dst");
     }
     for (int i = 0; i < d->n_terms; ++i) {
         if (d->term_ptrs_host[i] == nullptr) return fail(NI_ERR_INVALID, "ni_step: term %d pointer is NULL", i);
-        if (d->term_ptrs_host[i] == d->x_next) return fail(NI_ERR_INVALID, "ni_step: x_next aliases term %d", i);
+        if (d->term_ptrs_host[i] == d->x_next || d->term_ptrs_host[i] == d->x0_dst) return fail(NI_ERR_INVALID, "ni_step: x_next / x0_dst aliases term %d", i);
     }
     if (d->numel == 0) return NI_OK;
 
@@ -883,6 +904,7 @@ int ni_step(const NiStepDesc *d, void *stream)
     a.out0 = d->out0; a.out1 = d->out1;
     a.x0_dst = d->x0_dst; a.x_next = d->x_next; a.x_next_lp = d->x_next_lp; a.sumsq = d->sumsq;
     a.a = d->a; a.b0 = d->b0; a.b1 = d->b1; a.c_x0 = d->c_x0; a.c_xin = d->has_x0 ? d->c_xin : 0.f;
+    a.bias = d->bias; a.pixels = d->pixels_u8; a.px_scale = d->px_scale; a.px_shift = d->px_shift; a.px_channels = d->px_channels;
     a.k0 = (uint32_t)d->philox_seed; a.k1 = (uint32_t)(d->philox_seed >> 32);
     a.elem_offset = d->elem_offset;
     a.n_terms = d->n_terms; a.n_gen = d->n_gen;
@@ -891,7 +913,8 @@ int ni_step(const NiStepDesc *d, void *stream)
 
     // 128-bit path needs every pointer 16 B aligned (8 B for half outputs next to fp32 state) and vector-sized shapes
     const int VEC = 16 / ds;
-    bool vec_ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && aligned16(d->x_next) && (d->n_gen == 0 || d->elem_offset % 4 == 0);
+    bool vec_ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && (d->x_next == nullptr || aligned16(d->x_next)) && (d->n_gen == 0 || d->elem_offset % 4 == 0);
+    if (d->pixels_u8 != nullptr) vec_ok = vec_ok && (d->per_sample / d->px_channels) % VEC == 0; // a vector must stay inside one channel plane
     if (d->has_x0) {
         const uintptr_t omask = (uintptr_t)(VEC * dtype_size(od) - 1);
         vec_ok = vec_ok && d->out_sample_stride % VEC == 0 && (reinterpret_cast<uintptr_t>(d->out0) & omask) == 0 &&

@@ -93,7 +93,8 @@ class StepLaunch:
 
     def __init__(self, *, numel, per_sample, dtype, out_dtype=None, has_x0=True, x_in=0, out0=0, out1=0,
                  out_sample_stride=None, a=0.0, b0=0.0, b1=0.0, x0_dst=0, c_x0=0.0, c_xin=0.0,
-                 terms=(), gens=(), seed=0, elem_offset=0, accumulate=False, x_next=0, x_next_lp=0, lp_dtype=NI_BF16, sumsq=0):
+                 terms=(), gens=(), seed=0, elem_offset=0, accumulate=False, x_next=0, x_next_lp=0, lp_dtype=NI_BF16, sumsq=0,
+                 bias=0.0, pixels_u8=0, px_scale=0.5, px_shift=0.5, px_channels=0):
         """terms: iterable of (device_ptr, coeff); gens: iterable of (tensor_id, coeff, dst_ptr_or_0)."""
         terms = list(terms)
         gens = list(gens)
@@ -130,6 +131,9 @@ class StepLaunch:
         d.x_next_lp = x_next_lp or None
         d.lp_dtype = lp_dtype
         d.sumsq = sumsq or None
+        d.bias = float(bias)
+        d.pixels_u8 = pixels_u8 or None
+        d.px_scale, d.px_shift, d.px_channels = float(px_scale), float(px_shift), int(px_channels)
         self.desc = d
         self._keep = None
 

@@ -32,7 +32,7 @@ class NaturalInferenceSampler:
     def __init__(self, triple: CoeffTriple, io_scaling: Sequence[Tuple[float, float, float]], batch: int,
                  sample_shape: Sequence[int], *, device="cuda", dtype: torch.dtype = torch.float32, seed: int = 0,
                  eps0: str = "stored", lp_dtype: Optional[torch.dtype] = None, track_sumsq: bool = False,
-                 sample_offset: int = 0, keep_all_x0: bool = False, markov="auto"):
+                 sample_offset: int = 0, keep_all_x0: bool = False, markov="auto", final_scale: float = 1.0, final_bias: float = 0.0):
         """
         triple       coefficient matrices (A, B, node)
         io_scaling   K tuples (a_k, b0_k, b1_k): x0_k = a_k x_k + b0_k out0 + b1_k out1 (coeffs.io_*)
@@ -41,6 +41,9 @@ class NaturalInferenceSampler:
         eps0         "stored": the initial noise lives in a slot and is re-read by every row that uses it
                      "regen" : rows regenerate it in-kernel from (seed, tensor 0) -- no slot, no reads
         lp_dtype     also emit x_{k+1} in fp16/bf16 for a reduced-precision denoiser (fp32 state only)
+        final_scale, final_bias   output stage of latent models folded into the LAST step: x_K <- x_K*final_scale + final_bias
+                     (z/0.18215 of src/ValidateNaturalInference.py:368; z/scaling_factor + shift_factor of
+                     src/SD3NaturalInference.py:238).  The scale multiplies the last row's coefficients on the host, free.
         markov       "auto" | True | False.  First-order matrices (DDPM, DDIM, Euler, flow Euler; detected by
                      coeffs.markov_ratios to 1e-12) satisfy row_k = c_k*row_{k-1} + new terms, so the history sum
                      equals c_k*x_k and a step reads nothing but the model output and x_k: O(1) instead of O(k)
@@ -69,6 +72,7 @@ class NaturalInferenceSampler:
         self.eps0_mode = eps0
         self.lp_dtype = lp_dtype
         self.elem_offset = int(sample_offset) * self.per_sample
+        self.final_scale, self.final_bias = float(final_scale), float(final_bias)
         from .coeffs import markov_ratios
         use_markov = (markov_ratios(triple) is not None) if markov == "auto" else bool(markov)
         self.plan: StepPlan = build_plan(triple, keep_all_x0=keep_all_x0, markov=use_markov)
@@ -101,8 +105,8 @@ class NaturalInferenceSampler:
         return self._slab.numel() * self._slab.element_size()
 
     # ------------------------------------------------------------------ launch preparation
-    def _prepare(self, x_init_ptr: int, eps0_ptr: int, fresh_ptrs: Optional[Sequence[int]], out_ptr: int, stored0: bool):
-        key = (x_init_ptr, eps0_ptr, tuple(fresh_ptrs) if fresh_ptrs is not None else None, out_ptr, stored0)
+    def _prepare(self, x_init_ptr: int, eps0_ptr: int, fresh_ptrs: Optional[Sequence[int]], out_ptr: int, stored0: bool, pix_ptr: int = 0):
+        key = (x_init_ptr, eps0_ptr, tuple(fresh_ptrs) if fresh_ptrs is not None else None, out_ptr, stored0, pix_ptr)
         if self._launches is not None and key == self._launch_key:
             return
         if key in self._launch_cache:  # e.g. the two alternating staging buffers of sample_host_many
@@ -135,6 +139,18 @@ class NaturalInferenceSampler:
                     dst = self._eps_slots[s.fresh_slot].data_ptr() if s.keep_fresh else 0
                     gens.append((k + 1, s.fresh, dst))
             a, b0, b1 = self.io[k]
+            c_x0, c_xin, bias = s.c_x0, s.c_xin, 0.0
+            pix = 0
+            if k == self.K - 1:  # output stage folded into the last row
+                fs = self.final_scale
+                if fs != 1.0:
+                    terms = [(p_, c * fs) for p_, c in terms]
+                    gens = [(tid, c * fs, dst) for tid, c, dst in gens]
+                    c_x0, c_xin = c_x0 * fs, c_xin * fs
+                bias = self.final_bias
+                pix = pix_ptr
+                if pix:
+                    x_next = 0  # the uint8 image replaces x_K
             common = dict(numel=self.numel, per_sample=self.per_sample, dtype=code, seed=self.seed, elem_offset=self.elem_offset)
             chunks = [terms[i:i + NI_MAX_TERMS] for i in range(0, max(len(terms), 1), NI_MAX_TERMS)]
             row = []
@@ -142,8 +158,9 @@ class NaturalInferenceSampler:
                 last = ci == len(chunks) - 1
                 row.append(StepLaunch(
                     **common, has_x0=ci == 0, x_in=x_in if ci == 0 else 0, a=a, b0=b0, b1=b1,
-                    x0_dst=(self._x0_slots[s.x0_slot].data_ptr() if (s.keep_x0 and ci == 0) else 0), c_x0=s.c_x0,
-                    c_xin=s.c_xin if ci == 0 else 0.0,
+                    x0_dst=(self._x0_slots[s.x0_slot].data_ptr() if (s.keep_x0 and ci == 0) else 0), c_x0=c_x0,
+                    c_xin=c_xin if ci == 0 else 0.0, bias=bias if last else 0.0,
+                    pixels_u8=pix if last else 0, px_channels=self.sample_shape[0],
                     terms=chunk, gens=gens if ci == 0 else (), accumulate=ci > 0, x_next=x_next,
                     x_next_lp=(self._lp[(k + 1) % 2].data_ptr() if (self._lp is not None and last) else 0),
                     lp_dtype=DTYPE_CODE[self.lp_dtype] if self.lp_dtype else NI_BF16,
@@ -190,10 +207,12 @@ class NaturalInferenceSampler:
     # ------------------------------------------------------------------ the loop
     @torch.no_grad()
     def sample(self, denoiser: Callable, noise: Optional[torch.Tensor] = None, fresh_noise: Optional[Sequence[torch.Tensor]] = None,
-               out: Optional[torch.Tensor] = None, record: bool = False):
+               out: Optional[torch.Tensor] = None, record: bool = False, pixels_out: Optional[torch.Tensor] = None):
         """Run the K-step trajectory.  Returns x_K (a view of internal state unless `out` is given;
         valid until the next call).  With record=True returns (x_K, trace) where trace[k] has clones
-        of x0_k and x_{k+1} (needs keep_all_x0=True)."""
+        of x0_k and x_{k+1} (needs keep_all_x0=True).  With pixels_out ([B,H,W,C] uint8 CUDA tensor) the last step emits
+        the NHWC uint8 image directly (fused output stage, src/CIFAR10NaturalInference.py:308-309) and that tensor is
+        returned instead of x_K."""
         if record and any(s < 0 for s in self.plan.x0_slot_of):
             raise NiError("record=True needs a sampler built with keep_all_x0=True")
         shape = self.full_shape()
@@ -217,7 +236,15 @@ class NaturalInferenceSampler:
                 raise NiError("out must match the state shape/dtype and be a contiguous CUDA tensor")
             # caller-provided noise is always read through its pointer (it need not be the Philox tensor)
             stored0 = self.eps0_mode == "stored" or noise is not None
-            self._prepare(x_init.data_ptr(), eps0.data_ptr(), fresh_ptrs, out.data_ptr() if out is not None else 0, stored0)
+            if pixels_out is not None:
+                if len(self.sample_shape) != 3:
+                    raise NiError("pixels_out needs a (C,H,W) sample shape")
+                c_, h_, w_ = self.sample_shape
+                if (pixels_out.shape != (self.batch, h_, w_, c_) or pixels_out.dtype != torch.uint8 or not pixels_out.is_cuda
+                        or not pixels_out.is_contiguous() or record or out is not None or len(self.plan.steps) == 0):
+                    raise NiError("pixels_out must be a contiguous CUDA uint8 [B,H,W,C] tensor (and excludes out= / record=)")
+            self._prepare(x_init.data_ptr(), eps0.data_ptr(), fresh_ptrs, out.data_ptr() if out is not None else 0, stored0,
+                          pixels_out.data_ptr() if pixels_out is not None else 0)
             if self.sumsq is not None:
                 self.sumsq.zero_()
             st = stream_ptr(self.device)
@@ -230,6 +257,8 @@ class NaturalInferenceSampler:
                 x = (out if (k == self.K - 1 and out is not None) else self._X[(k + 1) % 2]).view(shape)
                 if record:
                     trace.append(dict(x0=self.x0_slot(k).clone(), x_next=x.clone()))
+        if pixels_out is not None:
+            return pixels_out
         return (x, trace) if record else x
 
     # ------------------------------------------------------------------ CUDA graph of the whole trajectory
@@ -268,12 +297,13 @@ class NaturalInferenceSampler:
             raise NiError("noise_host must be a CPU tensor matching the state shape/dtype")
         dev_noise = self._eps0.view(shape) if self.eps0_mode == "stored" else self._X[0].view(shape)
         dev_noise.copy_(noise_host, non_blocking=True)
-        x = self.sample(denoiser, noise=dev_noise)
         if pixels:
             if not hasattr(self, "_pix"):
                 b, (c, h, w) = self.batch, self.sample_shape
                 self._pix = torch.empty((b, h, w, c), dtype=torch.uint8, device=self.device)
-            x = to_pixel_u8(x, out=self._pix)
+            x = self.sample(denoiser, noise=dev_noise, pixels_out=self._pix)
+        else:
+            x = self.sample(denoiser, noise=dev_noise)
         out_host.copy_(x, non_blocking=True)
         return out_host
 
@@ -317,7 +347,7 @@ class NaturalInferenceSampler:
             if i >= 2:
                 main.wait_event(d_done[i - 2])                # batch i-2's result has left this output buffer
             if pixels:
-                to_pixel_u8(self.sample(denoiser, noise=nb), out=ob)
+                self.sample(denoiser, noise=nb, pixels_out=ob)
             else:
                 self.sample(denoiser, noise=nb, out=ob)
             c_done[i] = torch.cuda.Event()

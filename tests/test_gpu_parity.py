@@ -35,7 +35,7 @@ def rel_err(got, ref):
 def test_library_loaded_is_in_tree():
     from naturaldiffusion_b200 import _lib
     assert os.path.samefile(os.path.dirname(_lib.LIB_PATH), os.path.dirname(_lib.__file__))
-    assert ni.lib().ni_version() == 2
+    assert ni.lib().ni_version() == 3
 
 
 @pytest.mark.parametrize("numel,off", [(4096, 0), (4100, 0), (1000, 4), (1001, 7), (5, 1), (1 << 20, 1 << 33)])
@@ -307,6 +307,28 @@ def test_dropin_data_fn_and_install():
 
 
 # ------------------------------------------------------------------ output stage
+def test_fused_output_stage_in_last_step(weights_dir):
+    """f3: the last step can emit NHWC uint8 directly (same bytes as ni_to_pixel_u8 on x_K == the reference's
+    inverse scaler + to_pixel), and the latent un-scaling x/s + shift folds into the last row"""
+    den = lambda x, k: torch.tanh(0.7 * x) * (1.0 + 0.01 * k) + 0.1 * x
+    triple, s = _c2_sampler(weights_dir, 64)
+    x = s.sample(den).clone()
+    pix = torch.empty(64, 32, 32, 3, dtype=torch.uint8, device=DEV)
+    n0 = ni.launch_count()
+    got = s.sample(den, pixels_out=pix)
+    assert ni.launch_count() - n0 == triple.K + 1  # K steps + the Philox noise kernel; no separate pixel kernel
+    assert torch.equal(got, to_pixel_u8(x)) and np.array_equal(got.cpu().numpy(), O.to_pixel_u8(x.cpu()))
+    for variant in (2,):
+        from naturaldiffusion_b200 import _lib
+        try:
+            _lib.set_option("variant", variant)
+            assert torch.equal(s.sample(den, pixels_out=torch.empty_like(pix)), got)
+        finally:
+            _lib.set_option("variant", 0)
+    s2 = NaturalInferenceSampler(triple, io_score_vp(triple.node), 64, (3, 32, 32), device=DEV, seed=888, final_scale=1 / 0.18215, final_bias=0.0609)
+    assert rel_err(s2.sample(den), x / 0.18215 + 0.0609) < 1e-6
+
+
 def test_to_pixel_matches_reference_truncation():
     g = torch.Generator().manual_seed(0)
     x = torch.randn(16, 3, 32, 32, generator=g) * 0.8
