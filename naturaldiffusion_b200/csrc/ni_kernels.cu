@@ -871,6 +871,7 @@ int ni_step(const NiStepDesc *d, void *stream)
     if (d->numel % d->per_sample != 0) return fail(NI_ERR_INVALID, "ni_step: numel %lld is not a multiple of per_sample %lld", (long long)d->numel, (long long)d->per_sample);
     if (d->n_terms < 0 || d->n_terms > NI_MAX_TERMS) return fail(NI_ERR_TOO_MANY, "ni_step: n_terms=%d exceeds NI_MAX_TERMS=%d (chain launches with accumulate=1)", d->n_terms, NI_MAX_TERMS);
     if (d->n_gen < 0 || d->n_gen > NI_MAX_GEN) return fail(NI_ERR_TOO_MANY, "ni_step: n_gen=%d exceeds NI_MAX_GEN=%d", d->n_gen, NI_MAX_GEN);
+    if (d->numel == 0) return NI_OK; // an empty shard: nothing to do (its tensors have NULL data pointers)
     if (d->x_next == nullptr && d->pixels_u8 == nullptr) return fail(NI_ERR_INVALID, "ni_step: x_next is NULL (allowed only with pixels_u8)");
     if (d->pixels_u8 != nullptr && (d->px_channels <= 0 || d->per_sample % d->px_channels != 0)) return fail(NI_ERR_INVALID, "ni_step: pixels_u8 needs px_channels dividing per_sample");
     if (d->x_next == nullptr && (d->accumulate || d->x_next_lp != nullptr || d->sumsq != nullptr)) return fail(NI_ERR_INVALID, "ni_step: accumulate / x_next_lp / sumsq need x_next");

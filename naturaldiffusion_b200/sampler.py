@@ -174,6 +174,8 @@ class NaturalInferenceSampler:
     def _check_out(self, o: torch.Tensor, k: int):
         if not o.is_cuda:
             raise NiError(f"denoiser output at step {k} must be a CUDA tensor")
+        if self.batch == 0:
+            return
         if o.dim() < 2 or o.shape[0] != self.batch or o.numel() % self.batch != 0 or o.numel() // self.batch < self.per_sample:
             raise NiError(f"denoiser output at step {k} has shape {tuple(o.shape)}; expected [B={self.batch}, >= {self.per_sample} elements]")
 
@@ -190,7 +192,7 @@ class NaturalInferenceSampler:
         d = row[0].desc
         d.out0 = o0.data_ptr()
         d.out_dtype = DTYPE_CODE[o0.dtype]
-        d.out_sample_stride = o0.numel() // self.batch
+        d.out_sample_stride = o0.numel() // self.batch if self.batch else self.per_sample
         if len(outs) > 1 and outs[1] is not None:
             self._check_out(outs[1], k)
             if outs[1].dtype != o0.dtype or outs[1].shape != o0.shape:

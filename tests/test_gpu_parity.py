@@ -143,6 +143,39 @@ def test_fused_step_generated_noise_kept_and_lp():
     assert torch.equal(res["x_next_lp"], res["x_next"].to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("odt", [torch.float16, torch.bfloat16])
+def test_fused_step_reduced_precision_denoiser_io(odt):
+    """fp32 sampler state next to an fp16/bf16 denoiser: model outputs are read in their own dtype (8-byte vectors) and
+    x_{k+1} is emitted in fp32 and, fused, in the denoiser's dtype"""
+    g = torch.Generator().manual_seed(7)
+    shape = (6, 4, 16, 16)
+    x = torch.randn(shape, generator=g)
+    o0, o1 = torch.randn(shape, generator=g).to(odt), torch.randn(shape, generator=g).to(odt)
+    h = [torch.randn(shape, generator=g) for _ in range(3)]
+    res = fused_step(x_in=x.to(DEV), outs=[o0.to(DEV), o1.to(DEV)], a=1.2, b=[-0.8, 0.3], c_x0=0.7,
+                     terms=[(0.2, h[0].to(DEV)), (-0.4, h[1].to(DEV)), (0.9, h[2].to(DEV))], lp_dtype=odt)
+    x0 = 1.2 * x.double() - 0.8 * o0.double() + 0.3 * o1.double()
+    ref = 0.7 * x0 + 0.2 * h[0].double() - 0.4 * h[1].double() + 0.9 * h[2].double()
+    assert (res["x0"].cpu().double() - x0).abs().max() < 2e-6 and (res["x_next"].cpu().double() - ref).abs().max() < 3e-6
+    assert torch.equal(res["x_next_lp"], res["x_next"].to(odt))
+
+
+def test_edge_sizes_empty_batch_and_64bit_indexing(weights_dir):
+    """empty shard (a rank with no samples) is a no-op; element indices beyond 2^31 are addressed correctly"""
+    triple, s = _c2_sampler(weights_dir, 0)
+    assert s.sample(lambda x, k: x).shape == (0, 3, 32, 32)
+    n = (1 << 31) + 4096
+    src = torch.empty(n, dtype=torch.float16, device=DEV)
+    src[:8] = 1.0
+    src[-8:] = 3.0
+    src[(1 << 31) - 4:(1 << 31) + 4] = 2.0
+    out = weighted_sum_tensors([0.5], [src])
+    assert out[:8].eq(0.5).all() and out[-8:].eq(1.5).all() and out[(1 << 31) - 4:(1 << 31) + 4].eq(1.0).all()
+    del src, out
+    z = philox_normal((8,), seed=1, tensor_id=0, elem_offset=(1 << 40), device=DEV).cpu().numpy()
+    assert np.abs(z - philox.normal((8,), seed=1, tensor_id=0, elem_offset=(1 << 40))).max() < 4e-6
+
+
 def test_fused_step_long_row_chains_with_accumulate():
     """a dense 600-term row (> NI_MAX_TERMS) through the sampler's chunking"""
     from naturaldiffusion_b200.ops import StepLaunch, stream_ptr, DTYPE_CODE

@@ -245,3 +245,24 @@ def test_shard_range_partitions():
         assert spans[0][0] == 0 and spans[-1][1] == total
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
         assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_dropins_fit_the_reference_modules():
+    """(build container only) the real reference script modules expose exactly the names `dropin.install` replaces, with
+    call signatures the replacements accept"""
+    import inspect
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from naturaldiffusion_b200 import dropin
+    v, s3 = ref_loader.validate_module(), ref_loader.sd3_module()
+    data_fn, wsum = ref_loader.cifar_functions()
+    assert list(inspect.signature(v.weighted_sum).parameters) == ["weights", "seq_elem"]
+    assert list(inspect.signature(wsum).parameters) == ["past_x0_coeff", "seq_x0"]
+    assert list(inspect.signature(s3.weighted_sum).parameters) == ["seq_xstarts", "weights"]
+    assert list(inspect.signature(s3.euler_weighted_sum).parameters) == ["seq_xstarts", "cliplen"]
+    assert list(inspect.signature(data_fn).parameters) == list(inspect.signature(dropin.data_fn).parameters)
+    assert len(inspect.signature(dropin.weighted_sum).parameters) == 2
+    assert list(inspect.signature(dropin.euler_weighted_sum).parameters) == ["seq_xstarts", "cliplen"]
+    assert set(dropin.install(v)) == {"weighted_sum"} and v.weighted_sum is dropin.weighted_sum
+    assert set(dropin.install(s3)) == {"weighted_sum", "euler_weighted_sum"}
