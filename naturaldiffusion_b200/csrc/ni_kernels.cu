@@ -51,7 +51,7 @@ std::atomic<int> g_variant{0};       // 0 auto, 1 always the LDG kernel, 2 the T
 std::atomic<int> g_tma_max_stages{32};
 std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
-std::atomic<int> g_tma_ctas_per_sm{1};
+std::atomic<int> g_tma_ctas_per_sm{2};
 std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernel
 
 int fail(int code, const char *fmt, ...)
@@ -821,7 +821,19 @@ template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cuda
     TermTable<32> tab;
     memset(&tab, 0, sizeof(tab));
     for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-    ni_step_tma_kernel<T><<<(unsigned)grid, (nw + 1) * 32, smem, st>>>(a, tab, n_src, stages, ntiles);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)((nw + 1) * 32));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 0; // measured: PDL slows the persistent kernel down (profiles/r01_sweep.txt)
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, ni_step_tma_kernel<T>, a, tab, n_src, stages, ntiles);
+    }
     *used = true;
     return check_launch("ni_step (TMA) launch");
 }

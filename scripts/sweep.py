@@ -23,6 +23,14 @@ RUNS = [
     ("c3", ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=2"]),
 ]
 libs = [a for i, a in enumerate(sys.argv) if i > 0 and sys.argv[i - 1] == "--lib"] or [None]
+if "--tma2" in sys.argv:
+    RUNS = [("c2", ["--variant", "1"]), ("c3", ["--variant", "1"])]
+    for cfg in ("c2", "c3"):
+        for w in (8, 12, 16):
+            for c in (1, 2):
+                RUNS.append((cfg, ["--variant", "2", "--opt", f"tma_warps={w}", "--opt", f"tma_ctas_per_sm={c}"]))
+        RUNS.append((cfg, ["--variant", "2", "--opt", "tma_warps=16", "--opt", "tma_ctas_per_sm=2", "--opt", "tma_smem_kb=226"]))
+        RUNS.append((cfg, ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=3"]))
 if "--pdl" in sys.argv:
     RUNS = [(c, ["--opt", f"pdl={v}"] + e) for c, e in (("c2", []), ("c3", []), ("c4", []), ("c5", []), ("c5", ["--batch", "4"])) for v in (0, 1)]
 if "--ldg-only" in sys.argv:
