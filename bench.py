@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager-comparator", action="store_true", help="also time the reference's eager torch loop on this GPU (c2/c3)")
     ap.add_argument("--markov", default="auto", choices=["auto", "0", "1"], help="first-order fast path (c4/c5): auto|0|1")
     args = ap.parse_args()
     if args.steps is None:
@@ -327,6 +328,43 @@ def run_ours(args, rank, world, local_rank):
                "d2h_bytes_per_step": out_h.numel() * out_h.element_size(), "steps": n_e2e, "ms_per_step": ems / n_e2e,
                "api": f"NaturalInferenceSampler.sample_host_many(pixels={pixels}), double-buffered copy streams: pinned {dts} noise in, " + ("NHWC uint8 out" if pixels else f"{dts} latent out")}
 
+    # ---- optional comparator: the reference's own loop structure (oracle restatement: fp64 history, one torch kernel
+    # per op, per-step H2D scalars) on THIS GPU with the same null denoiser -- "eager torch on B200", SURVEY 2.3
+    eager = None
+    if args.eager_comparator and args.config in ("c2", "c3") and world == 1:
+        from oracle import ni_oracle as O
+        A_, B_, node_ = O.load_triple(os.path.join(WEIGHTS, fname))
+
+        def eager_traj():
+            seq, x = [], noise
+            for kk in range(K):
+                vec_t = node_[kk, 0] * torch.ones(batch, device=dev)
+                score = -outs[0] / O.vp_marginal_std(vec_t)[:, None, None, None]
+                x64, s64 = x.to(torch.float64), score.to(torch.float64)
+                e_ = torch.tensor(node_[kk, 2], dtype=torch.float64, device=dev)
+                a_ = torch.tensor(node_[kk, 1], dtype=torch.float64, device=dev)
+                seq.append((s64 * e_ ** 2 + x64) / a_)
+                acc = torch.zeros_like(seq[0])
+                for ii, x0 in enumerate(seq):
+                    acc += x0 * A_[kk][ii]
+                x = acc.to(torch.float32) + B_[kk, 0] * noise
+            return x
+
+        for _ in range(2):
+            eager_traj()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            xe = eager_traj()
+        g1.record()
+        torch.cuda.synchronize()
+        gms = g0.elapsed_time(g1) / 5
+        mine = sampler.sample(den, noise=noise)
+        eager = {"ms_per_step": gms, "value": batch / (gms * 1e-3), "unit": "samples/s", "speedup_of_fused_step": gms / ms_per_step,
+                 "max_abs_diff_over_norm": float((mine - xe).abs().max() / xe.norm()),
+                 "what": "reference loop structure (fp64 history, eager torch ops) on the same B200, same null denoiser"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -360,6 +398,8 @@ def run_ours(args, rank, world, local_rank):
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
     }
+    if eager is not None:
+        line["reference_eager_gpu"] = eager
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
