@@ -217,3 +217,40 @@ def dpm_solver_pp_2m_triple(K: int, grid="time_quadratic", t_T=1.0, t_0=1e-3) ->
             nxt = nxt - 0.5 * phi * (1.0 / r0) * (y - prev_y)
         prev_y, prev_t, x = y, s, nxt
     return tr.finish(x, ts[-1], name=f"dpmsolverpp2m_{K:03d}")
+
+
+def deis_tab_triple(K: int, ab_order: int = 3, t_T=1.0, t_0=1e-3, quad_points: int = 10000) -> CoeffTriple:
+    """DEIS tAB-`ab_order` (exponential integrator, Adams-Bashforth in t) on the quadratic time grid, VP linear schedule:
+        x_{i+1} = psi(t_i, t_{i+1}) x_i + sum_j C_ij eps(x_{i-j}, t_{i-j}),  order min(i, ab_order) at step i,
+        C_ij = int_{t_i}^{t_{i+1}} psi(tau, t_{i+1}) * (-1/2 dlog(abar)/dtau / sqrt(1 - abar(tau))) * L_j(tau) dtau
+    with L_j the Lagrange basis on (t_{i-o}..t_i) and the integral a left Riemann sum of `quad_points` points, exactly as
+    deps/th_deis/multistep.py:6-96 + vpsde.py:39-63 evaluate it (there in jax float32; here float64).  The matrix the
+    reference derives with sympy + jax in src/AnalyzeDEIS.py:90-138 (results/deis/deis_tab_*.npz)."""
+    b0, b1 = 0.1, 20.0
+    ns = VPLinearSchedule(b0, b1)
+    ts = quadratic_time_grid(K, t_T, t_0)
+    log_abar = lambda t: 2.0 * ns.log_alpha(t)
+    abar = lambda t: np.exp(log_abar(t))
+    dlog = lambda t: -t * (b1 - b0) - b0
+    tr = CoefficientTracer(K, ns)
+    x = tr.noise()
+    eps_hist = []  # newest first
+    for i in range(K):
+        s, t = ts[i], ts[i + 1]
+        o = min(i, ab_order)
+        eps_hist.insert(0, tr.model_eps(x, s))
+        tau = np.linspace(s, t, quad_points, endpoint=False)
+        dt = (t - s) / quad_points
+        integrand = np.sqrt(abar(t) / abar(tau)) * (-0.5 * dlog(tau) / np.sqrt(1.0 - abar(tau)))
+        nodes = ts[i - o: i + 1]  # t_{i-o} .. t_i
+        nxt = np.sqrt(abar(t) / abar(s)) * x
+        for j in range(o + 1):
+            idx = o - j  # node of eps_{i-j}
+            num = tau[:, None] - nodes[None, :]
+            den = nodes[idx] - nodes
+            num[:, idx], den[idx] = 1.0, 1.0
+            poly = np.prod(num, axis=1) / np.prod(den)
+            nxt = nxt + float(np.sum(integrand * poly) * dt) * eps_hist[j]
+        eps_hist = eps_hist[:ab_order]
+        x = nxt
+    return tr.finish(x, ts[-1], name=f"deis_tab_{K:03d}")

@@ -459,3 +459,49 @@ def dpmpp_2m_original_loop(ts, eps_model, noise):
             nxt = nxt - 0.5 * (a_t * phi) * ((1.0 / r0) * (m - prev_m))
         prev_m, prev_t, x = m, s, nxt
     return x
+
+
+# --------------------------------------------------------------------------------------
+# DEIS tAB3, the original multistep sampler (comparator for the generated matrix)
+# --------------------------------------------------------------------------------------
+
+
+def deis_tab_coefficients(ts, ab_order=3, num_item=10000, b0=0.1, b1=20.0):
+    """[x_coef, C_0..C_ab_order] per step, as deps/th_deis/multistep.py:6-96 builds `ab_coef` (get_ab_eps_coef with the
+    order ramp 0,1,..,ab_order; left Riemann sum with num_item points; VPSDE.psi / eps_integrand of
+    deps/th_deis/vpsde.py:57-63 for the linear-beta alpha of :13-19), float64 numpy instead of jax float32."""
+    ts = np.asarray(ts, dtype=np.float64)
+    la = lambda t: 2.0 * (-0.25 * t**2 * (b1 - b0) - 0.5 * t * b0)
+    coef = np.zeros((len(ts) - 1, ab_order + 2))
+    for i in range(len(ts) - 1):
+        t_start, t_end = ts[i], ts[i + 1]
+        order = min(i, ab_order)
+        coef[i, 0] = np.sqrt(np.exp(la(t_end) - la(t_start)))
+        t_inter = np.linspace(t_start, t_end, num_item, endpoint=False)
+        dt = (t_end - t_start) / num_item
+        psi = np.sqrt(np.exp(la(t_end) - la(t_inter)))
+        integrand = psi * (-0.5 * (-t_inter * (b1 - b0) - b0) / np.sqrt(1 - np.exp(la(t_inter))))
+        ts_poly = ts[i - order: i + 1]
+        for out_j, coef_idx in enumerate(range(order, -1, -1)):  # "we do flip of j here"
+            poly = np.ones_like(t_inter)
+            for k in range(order + 1):
+                if k != coef_idx:
+                    poly *= (t_inter - ts_poly[k]) / (ts_poly[coef_idx] - ts_poly[k])
+            coef[i, 1 + out_j] = np.sum(integrand * poly) * dt
+    return coef
+
+
+@torch.no_grad()
+def deis_tab_original_loop(ts, eps_model, noise, ab_order=3):
+    """th_deis tAB sampler (deps/th_deis/multistep.py:98-104 `ab_step`, driven as in src/AnalyzeDEIS.py:42-58)."""
+    coef = torch.from_numpy(deis_tab_coefficients(ts, ab_order)).to(torch.float32)
+    x = noise.clone()
+    eps_pred = [x] * ab_order
+    for i in range(len(ts) - 1):
+        new_eps = eps_model(x, float(ts[i]))
+        full = [new_eps, *eps_pred]
+        nxt = coef[i, 0] * x
+        for c, e in zip(coef[i, 1:], full):
+            nxt = nxt + c * e
+        x, eps_pred = nxt, full[:-1]
+    return x

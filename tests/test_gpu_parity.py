@@ -597,3 +597,22 @@ def test_random_sparse_matrices_ring_buffer_vs_fp64_oracle(seed):
         hist.append(x0)
         xk = xk.float().double()
         assert rel_err(trace[k]["x0"], x0) < 2e-6 and rel_err(trace[k]["x_next"], xk) < 2e-6, (seed, k)
+
+
+def test_deis_tab3_matrix_equals_original_sampler():
+    """DEIS tAB3, 15 steps on the quadratic grid (the other sampler BASELINE config 3 names): generated matrix through
+    the fused step vs the original exponential-integrator multistep loop (oracle restatement of th_deis)"""
+    from naturaldiffusion_b200.generators import VPLinearSchedule, deis_tab_triple
+    K, B = 15, 256
+    triple = deis_tab_triple(K)
+    ns = VPLinearSchedule()
+    ts = triple.node[:, 0]
+    io = [(1.0 / ns.alpha(t), -ns.sigma(t) / ns.alpha(t), 0.0) for t in ts[:-1]]
+    net = ToyEps(3, seed=11, t_scale=0.3)
+    eps_model = lambda x, t: float(ns.sigma(t)) * x + 0.1 * net(x, float(t))
+    s = NaturalInferenceSampler(triple, io, B, (3, 32, 32), device=DEV, seed=6)
+    assert not s.plan.markov
+    x = s.sample(lambda z, k: eps_model(z, ts[k]))
+    noise = philox_normal((B, 3, 32, 32), seed=6, tensor_id=0, device=DEV)
+    xo = O.deis_tab_original_loop(ts, eps_model, noise)
+    assert float(xo.abs().max()) < 50 and rel_err(x, xo) < 1e-5

@@ -228,6 +228,19 @@ def test_coefficient_space_tracer_reproduces_reference_dpm_solver_matrices(golde
     assert markov_ratios(d) is not None and np.abs(d.A.sum(1) + d.B[:, 0] * 0 - d.node[1:, 1]).max() < 7e-3
 
 
+def test_deis_generator_matches_reference_matrices(golden_dir):
+    """DEIS tAB3 on the quadratic grid (the reference needs jax for it, src/AnalyzeDEIS.py): float64 numpy restatement of
+    the same Riemann-sum coefficients reproduces results/deis/deis_tab_{100,200} to the jax-float32 noise of the files"""
+    m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
+    for K in (100, 200):
+        t = generators.deis_tab_triple(K)
+        key = f"deis/deis_tab_{K:03d}"
+        assert np.abs(t.A - m[key + "/A"]).max() < 1e-5 and np.abs(t.B - m[key + "/B"]).max() < 1e-5
+        assert np.abs(t.node - m[key + "/node"]).max() < 1e-6
+    c = O.deis_tab_coefficients(generators.quadratic_time_grid(15))
+    assert c.shape == (15, 5) and np.all(c[0, 2:] == 0) and np.all(c[1, 3:] == 0) and c[5, 4] != 0  # order ramp 0,1,2,3
+
+
 def test_schedule_helpers():
     assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
     assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
