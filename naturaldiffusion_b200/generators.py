@@ -254,3 +254,79 @@ def deis_tab_triple(K: int, ab_order: int = 3, t_T=1.0, t_0=1e-3, quad_points: i
         eps_hist = eps_hist[:ab_order]
         x = nxt
     return tr.finish(x, ts[-1], name=f"deis_tab_{K:03d}")
+
+
+def _vp_euler_grid(num_step: int):
+    n = num_step + 1
+    return 1.0 + np.arange(n) * (1.0 / n - 1.0) / (n - 1), (1.0 / n - 1.0) / (n - 1)
+
+
+def vp_euler_triple(num_step: int, kind: str = "ode") -> CoeffTriple:
+    """Euler discretisations of the VP SDE on the uniform grid t: 1 -> 1/(K+1) with the score written through the
+    x0-prediction, score = (alpha*y - x)/sigma^2 (src/AnalyzeEulerHeun.py:50-123 probability-flow ODE, :125-201
+    Euler-Maruyama reverse SDE, :203-290 Heun).  kind: "ode" | "sde" | "heun" (2 model calls per step -> 2K rows).
+    "heun" keeps the reference's second-stage quirk (alpha of the START node multiplies the second prediction,
+    :249) so that the shipped ode_heun_* matrices are reproduced; pass kind="heun_exact" for the textbook update."""
+    ns = VPLinearSchedule()
+    ts, dt = _vp_euler_grid(num_step)
+    beta = lambda t: ns.b0 + t * (ns.b1 - ns.b0)
+    calls = 2 * num_step if kind.startswith("heun") else num_step
+    tr = CoefficientTracer(calls, ns)
+    x = tr.noise()
+
+    def velocity(xv, y, t, alpha_t, half):
+        score = (alpha_t * y - xv) / ns.sigma(t) ** 2
+        return -0.5 * beta(t) * xv - (0.5 if half else 1.0) * beta(t) * score
+
+    for i in range(num_step):
+        s, t = ts[i], ts[i + 1]
+        y_s = tr.model_x0(x, s)
+        if kind == "ode":
+            x = x + velocity(x, y_s, s, ns.alpha(s), True) * dt
+        elif kind == "sde":
+            x = x + velocity(x, y_s, s, ns.alpha(s), False) * dt + np.sqrt(beta(s)) * np.sqrt(abs(dt)) * tr.noise()
+        else:
+            v_s = velocity(x, y_s, s, ns.alpha(s), True)
+            x_hat = x + v_s * dt
+            y_hat = tr.model_x0(x_hat, t + 0.0005)  # the reference tags the predictor node with a tiny time offset
+            a2 = ns.alpha(s) if kind == "heun" else ns.alpha(t)
+            score_t = (a2 * y_hat - x_hat) / ns.sigma(t) ** 2
+            v_t = -0.5 * beta(t) * x_hat - 0.5 * beta(t) * score_t
+            x = x + 0.5 * (v_s + v_t) * dt
+    name = {"ode": "ode_euler", "sde": "sde_euler"}.get(kind, "ode_heun")
+    return tr.finish(x, ts[-1], name=f"{name}_{calls:03d}")
+
+
+def dpm_solver_3s_triple(steps: int, plus_plus: bool = False, t_T=1.0, t_0=1e-3) -> CoeffTriple:
+    """Singlestep third-order DPM-Solver-3 (noise prediction) / DPM-Solver++(3S) (data prediction) on a uniform time
+    grid, r1 = 1/3, r2 = 2/3, 3 model calls per step -> K = 3*steps rows, with the update formulas exactly as the
+    reference analyses them (src/AnalyzeDPMSolver.py:431-547 and :550-695 -- note the ++ variant there subtracts the
+    difference terms; the shipped results/dpmsolverpp/dpmsolverpp3s_* matrices are reproduced as they are)."""
+    ns = VPLinearSchedule()
+    ts = np.linspace(t_T, t_0, steps + 1)
+    r1, r2 = 1.0 / 3.0, 2.0 / 3.0
+    tr = CoefficientTracer(3 * steps, ns)
+    x = tr.noise()
+    for i in range(steps):
+        s, t = ts[i], ts[i + 1]
+        h = ns.lam(t) - ns.lam(s)
+        s1, s2 = ns.inv_lam(ns.lam(s) + r1 * h), ns.inv_lam(ns.lam(s) + r2 * h)
+        if plus_plus:
+            m_s = tr.model_x0(x, s)
+            x_s1 = ns.sigma(s1) / ns.sigma(s) * x - ns.alpha(s1) * np.expm1(-r1 * h) * m_s
+            m_s1 = tr.model_x0(x_s1, s1)
+            x_s2 = (ns.sigma(s2) / ns.sigma(s) * x - ns.alpha(s2) * np.expm1(-r2 * h) * m_s
+                    - (r2 / r1) * ns.alpha(s2) * (np.expm1(-r2 * h) / (r2 * h) + 1.0) * (m_s1 - m_s))
+            m_s2 = tr.model_x0(x_s2, s2)
+            x = (ns.sigma(t) / ns.sigma(s) * x - ns.alpha(t) * np.expm1(-h) * m_s
+                 - (1.0 / r2) * ns.alpha(t) * (np.expm1(-h) / h + 1.0) * (m_s2 - m_s))
+        else:
+            e_s = tr.model_eps(x, s)
+            x_s1 = np.exp(ns.log_alpha(s1) - ns.log_alpha(s)) * x - ns.sigma(s1) * np.expm1(r1 * h) * e_s
+            e_s1 = tr.model_eps(x_s1, s1)
+            x_s2 = (np.exp(ns.log_alpha(s2) - ns.log_alpha(s)) * x - ns.sigma(s2) * np.expm1(r2 * h) * e_s
+                    - (r2 / r1) * ns.sigma(s2) * (np.expm1(r2 * h) / (r2 * h) - 1.0) * (e_s1 - e_s))
+            e_s2 = tr.model_eps(x_s2, s2)
+            x = (np.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - ns.sigma(t) * np.expm1(h) * e_s
+                 - (1.0 / r2) * ns.sigma(t) * (np.expm1(h) / h - 1.0) * (e_s2 - e_s))
+    return tr.finish(x, ts[-1], name=("dpmsolverpp3s" if plus_plus else "dpmsolver3s") + f"_{3 * steps:03d}")

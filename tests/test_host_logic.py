@@ -241,6 +241,42 @@ def test_deis_generator_matches_reference_matrices(golden_dir):
     assert c.shape == (15, 5) and np.all(c[0, 2:] == 0) and np.all(c[1, 3:] == 0) and c[5, 4] != 0  # order ramp 0,1,2,3
 
 
+def test_every_shipped_matrix_is_reproduced(golden_dir):
+    """all 46 coefficient matrices under the reference's results/ (every sampler family it analyses: DDPM, DDIM, VP
+    ODE/SDE Euler, Heun, DPM-Solver-2S/3S, DPM-Solver++(2S/3S), DEIS tAB3, flow Euler) come out of generators.py"""
+    m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
+    fam = {
+        "ddim/ddim": lambda K: generators.ddim_triple(K), "ddpm/ddpm": lambda K: generators.ddpm_triple(K),
+        "ddpm/ddpm_sympy": lambda K: generators.ddpm_triple(K), "deis/deis_tab": lambda K: generators.deis_tab_triple(K),
+        "dpmsolver/dpmsolver2s": lambda K: generators.dpm_solver_2s_triple(K // 2),
+        "dpmsolver/dpmsolver3s": lambda K: generators.dpm_solver_3s_triple(K // 3),
+        "dpmsolverpp/dpmsolverpp2s": lambda K: generators.dpm_solver_pp_2s_triple(K // 2),
+        "dpmsolverpp/dpmsolverpp3s": lambda K: generators.dpm_solver_3s_triple(K // 3, plus_plus=True),
+        "euler_heun/ode_euler": lambda K: generators.vp_euler_triple(K, "ode"),
+        "euler_heun/sde_euler": lambda K: generators.vp_euler_triple(K, "sde"),
+        "euler_heun/ode_heun": lambda K: generators.vp_euler_triple(K // 2, "heun"),
+        "flow_euler/flow_euler_simpy": lambda K: generators.flow_euler_triple(K),
+    }
+    keys = sorted({k.rsplit("/", 1)[0] for k in m.files if k.endswith("/A")})
+    done = 0
+    for key in keys:
+        name, K = key.rsplit("_", 1)
+        t = fam[name](int(K))
+        tol = 1e-5 if "deis" in key else 1e-12  # the DEIS files carry jax-float32 quadrature noise
+        assert np.abs(t.A - m[key + "/A"]).max() < tol and np.abs(t.B - m[key + "/B"]).max() < tol, key
+        node_ref = m[key + "/node"].copy()
+        if "sympy" in key:
+            node_ref[0, 1] = t.node[0, 1]  # closed form vs sympy differ only in node[0,1] (SURVEY appendix D.5)
+        assert np.abs(t.node - node_ref).max() < max(tol, 1e-6), key
+        done += 1
+    for famname, fn in (("ddim", generators.ddim_triple), ("ddpm", generators.ddpm_triple)):  # the two K=500 files, by digest
+        t = fn(500)
+        d = np.concatenate([t.A.sum(0), t.A.sum(1), t.B.sum(0), t.B.sum(1), np.diag(t.A), t.node.ravel()])
+        assert np.abs(d - m[f"{famname}/{famname}_500/digest"]).max() < 1e-11
+        done += 1
+    assert done == 46
+
+
 def test_schedule_helpers():
     assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
     assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
