@@ -15,7 +15,7 @@ Pinning: ``tests/golden/make_golden.py`` imports the reference's *own* functions
 from /root/reference (third-party modules stubbed, see ``oracle/ref_loader.py``),
 runs them on seeded inputs and commits the outputs under ``tests/golden/``;
 ``tests/test_oracle_golden.py`` checks this restatement against those vectors
-and against the 46 shipped coefficient matrices.  Parity is therefore pinned.
+and against the shipped coefficient matrices (44 under results/).  Parity is therefore pinned.
 """
 from __future__ import annotations
 
