@@ -616,3 +616,23 @@ def test_deis_tab3_matrix_equals_original_sampler():
     noise = philox_normal((B, 3, 32, 32), seed=6, tensor_id=0, device=DEV)
     xo = O.deis_tab_original_loop(ts, eps_model, noise)
     assert float(xo.abs().max()) < 50 and rel_err(x, xo) < 1e-5
+
+
+def test_c_abi_from_plain_cpp_without_torch(tmp_path):
+    """the boundary is a real C ABI: examples/c_abi_demo.cu (plain C++/CUDA runtime, no Python, no torch) links only
+    libni_b200.so, runs a 3-step trajectory with history, Philox noise and the fused uint8 stage, and checks it on the host"""
+    import shutil
+    import subprocess
+    from naturaldiffusion_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_abi_demo.cu"), "-o", exe, "-L", libdir, "-lni_b200",
+                    "-Xlinker", "-rpath", "-Xlinker", libdir], check=True, capture_output=True)
+    ldd = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libni_b200" in ldd and "torch" not in ldd and "python" not in ldd
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pixel mismatches = 0" in r.stdout
