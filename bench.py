@@ -299,6 +299,32 @@ def run_ours(args, rank, world, local_rank):
     achieved = bytes_per_traj / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU == per launch (only ni_step kernels run)
     peak, peak_src = measured_peak()
 
+    # ---- cold-L2 check: every launch timed on its own with the L2 flushed right before it (a 512 MB READ sweep, which
+    # leaves clean lines -- a memset would leave 126 MB of dirty lines to be written back during the timed kernel), so no
+    # launch can find the previous step's stores in the 126 MB L2 (the null denoiser leaves nothing between steps)
+    cold = None
+    if world == 1 and args.config in ("c2", "c3"):
+        flush = torch.zeros(128 << 20, dtype=torch.float32, device=dev)
+        sampler._graph = None
+        sampler.sample(den, noise=noise)
+        evs = []
+        n_cold = 5
+        st_ptr = torch.cuda.current_stream(dev).cuda_stream
+        for _ in range(n_cold):
+            for k in range(K):
+                flush.max()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                sampler.step(k, outs[0] if m == 1 else outs, st_ptr)
+                b_.record()
+                evs.append((a_, b_))
+        torch.cuda.synchronize()
+        cold_ms = sum(a_.elapsed_time(b_) for a_, b_ in evs) / n_cold
+        cold = {"ms_per_trajectory": cold_ms, "achieved": bytes_per_traj / (cold_ms * 1e-3) / 1e9,
+                "frac": bytes_per_traj / (cold_ms * 1e-3) / 1e9 / measured_peak()[0],
+                "how": "each launch bracketed by its own CUDA events after a 512 MB read sweep (L2 flush); includes ~2 us event overhead per launch, no graph / PDL overlap"}
+        del flush
+
     # ---- end-to-end arm: host buffers through the public sampler API
     e2e = None
     if not args.no_e2e:
@@ -395,7 +421,7 @@ def run_ours(args, rank, world, local_rank):
                      "traffic": ncu_traffic(args.config, args.eps0), "peak_source": peak_src,
                      "kernel": "ni_step_kernel (direct-load)" if args.variant != 2 else "ni_step_tma_kernel", "algorithmic_bytes_per_launch": bytes_per_traj / launches_per_traj,
                      "tensor_transfers_per_trajectory": units, "us_per_launch": 1e3 * ms_per_step / launches_per_traj,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "frac_of_nominal_8TBs": achieved / 8000.0, "cold_l2": cold},
         "cpu_baseline": cpu,
     }
     if eager is not None:
