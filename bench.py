@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--eager-comparator", action="store_true", help="also time the reference's eager torch loop on this GPU (c2/c3)")
     ap.add_argument("--markov", default="auto", choices=["auto", "0", "1"], help="first-order fast path (c4/c5): auto|0|1")
     args = ap.parse_args()
@@ -220,6 +221,8 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from naturaldiffusion_b200.hostutil import bind_to_gpu_numa_node
+    numa_cpus = None if args.no_numa else bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -411,7 +414,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"{args.config}: NI update, {fname}, batch {batch}/GPU x {list(shape)}, K={K} fused steps per trajectory, "
                                f"null denoiser ({m} pre-generated N(0,1) model output(s) of {cout} channels re-read from HBM each step)",
                    "markov_fast_path": bool(sampler.plan.markov),
-                   "shape": [batch] + list(shape), "eps0": args.eps0, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
+                   "shape": [batch] + list(shape), "eps0": args.eps0, "numa_bound_cpus": numa_cpus, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
                    "l2": f"inputs larger than L2: per-trajectory working set {(sampler.state_bytes() + sum(o.numel() for o in outs) * esize) / 1e6:.0f} MB vs 126 MB L2",
                    "state_bytes": sampler.state_bytes()},
         "clocks": clk,
