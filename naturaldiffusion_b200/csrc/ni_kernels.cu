@@ -613,13 +613,6 @@ template <int CAP> struct WsumTable {
     double c[CAP];
 };
 
-template <typename TS> struct SrcIO {
-    template <int VEC> static __device__ __forceinline__ void load(const void *p, int64_t e, float (&f)[VEC])
-    {
-        unpack<TS, VEC>(load_raw<TS, VEC>(static_cast<const TS *>(p) + e), f);
-    }
-};
-
 template <typename TS, typename TD, int VEC, int CAP>
 __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant__ WsumTable<CAP> tab, int n, void *dst, int64_t nvec, double scale)
 {
