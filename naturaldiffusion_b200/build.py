@@ -50,6 +50,21 @@ def build(force: bool = False, defines=(), out: str = OUT, verbose: bool = False
     return out
 
 
+def build_demo() -> str:
+    """examples/c_abi_demo.cu -> build/c_abi_demo (plain C++ client of the C ABI; run by the GPU tests)."""
+    src = os.path.join(ROOT, "examples", "c_abi_demo.cu")
+    exe = os.path.join(ROOT, "build", "c_abi_demo")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if os.path.isfile(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(p) for p in (src, HDR, OUT)):
+        return exe
+    cmd = [find_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", HERE, "-lni_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../naturaldiffusion_b200"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on the C-ABI demo:\n" + r.stdout + r.stderr)
+    return exe
+
+
 def build_oracle() -> str:
     """The C part of the CPU oracle (test infrastructure) -- gcc only."""
     d = os.path.join(ROOT, "oracle")

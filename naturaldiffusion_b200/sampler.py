@@ -93,6 +93,17 @@ class NaturalInferenceSampler:
         self._graph_out = None
         self.kernel_launches_per_trajectory = sum(p.launches(k, eps0 == "stored") for k in range(self.K))
 
+    def set_sample_offset(self, sample_offset: int):
+        """Re-target this sampler at another batch of a larger run: batch `[sample_offset, sample_offset + B)` of the
+        global sample index space.  In-kernel noise is keyed by the global element index, so a run split into batches
+        (or ranks) of any size draws the same samples."""
+        off = int(sample_offset) * self.per_sample
+        if off != self.elem_offset:
+            self.elem_offset = off
+            self._launch_cache.clear()
+            self._launches = self._launch_key = None
+            self._graph = None
+
     # ------------------------------------------------------------------ views
     def full_shape(self):
         return (self.batch,) + self.sample_shape
