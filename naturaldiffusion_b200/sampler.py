@@ -160,10 +160,10 @@ class NaturalInferenceSampler:
                     c_x0, c_xin = c_x0 * fs, c_xin * fs
                 bias = self.final_bias
                 pix = pix_ptr
-                if pix:
-                    x_next = 0  # the uint8 image replaces x_K
             common = dict(numel=self.numel, per_sample=self.per_sample, dtype=code, seed=self.seed, elem_offset=self.elem_offset)
             chunks = [terms[i:i + NI_MAX_TERMS] for i in range(0, max(len(terms), 1), NI_MAX_TERMS)]
+            if pix and len(chunks) == 1:
+                x_next = 0  # the uint8 image replaces x_K (a chained >512-term row still needs x_K to accumulate into)
             row = []
             for ci, chunk in enumerate(chunks):
                 last = ci == len(chunks) - 1

@@ -645,3 +645,22 @@ def test_cifar10_pipeline_example_is_batching_invariant():
     assert a["n"] == b["n"] == 96
     assert np.abs(a["mu"] - b["mu"]).max() < 1e-4 and np.abs(a["sigma"] - b["sigma"]).max() < 1e-4
     assert np.isfinite(a["fid"]) and abs(a["fid"] - b["fid"]) < 1e-2 * max(1.0, abs(b["fid"]))
+
+
+def test_sd3_flow_euler_matrix_equals_vanilla_euler():
+    """src/SD3NaturalInference.py:81-154: Natural Inference with the Euler-equivalent weights (sigma_i - sigma_{i+1}) is
+    the vanilla flow-matching Euler update (`is_vanilla_update=True`, :126-127).  Here: the exact flow-Euler matrix on the
+    SD3 sigma grid through the fused step (first-order path, CFG 7 on two velocity outputs) vs the vanilla Euler loop."""
+    from naturaldiffusion_b200.generators import flow_euler_triple
+    sig = O.sd3_sigmas().astype(np.float64)
+    triple = flow_euler_triple(28, sigmas=sig)
+    net = ToyEps(16, seed=5)
+    den = lambda x, k: (net(x, 1000 * float(sig[k]), 0), net(x, 1000 * float(sig[k]), 1))
+    s = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), 3, (16, 16, 16), device=DEV, seed=10)
+    assert s.plan.markov and s.plan.total_units(2) == 28 * 4
+    x = s.sample(den).clone()
+    noise = philox_normal((3, 16, 16, 16), seed=10, tensor_id=0, device=DEV)
+    ref = O.sd3_euler_original_loop(sig, den, noise)
+    assert rel_err(x, ref) < 2e-6
+    dense = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), 3, (16, 16, 16), device=DEV, seed=10, markov=False)
+    assert rel_err(dense.sample(den), ref) < 2e-6
