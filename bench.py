@@ -348,6 +348,15 @@ def run_ours(args, rank, world, local_rank):
         e2e_sampler.sample_host_many(den, [noise_hs[i % 2] for i in range(n_e2e)], [out_hs[i % 2] for i in range(n_e2e)], pixels=pixels)
         s1.record()
         barrier()
+        # informational: the reference's own data flow (noise drawn on the device from a seed, only images come back)
+        e2e_sampler.sample_host_many(den, None, [out_hs[i % 2] for i in range(4)], pixels=pixels, first_sample=rank * batch)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        e2e_sampler.sample_host_many(den, None, [out_hs[i % 2] for i in range(n_e2e)], pixels=pixels, first_sample=rank * batch)
+        q1.record()
+        barrier()
+        seeded_ms = q0.elapsed_time(q1)
         ems = s0.elapsed_time(s1)
         if world > 1:
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
@@ -355,6 +364,9 @@ def run_ours(args, rank, world, local_rank):
             ems = t.item()
         e2e = {"value": world * batch * n_e2e / (ems * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": noise_h.numel() * noise_h.element_size(),
                "d2h_bytes_per_step": out_h.numel() * out_h.element_size(), "steps": n_e2e, "ms_per_step": ems / n_e2e,
+               "seeded_variant": {"value": batch * n_e2e / (seeded_ms * 1e-3), "ms_per_step": seeded_ms / n_e2e, "h2d_bytes_per_step": 0,
+                                  "note": "this rank only; noise drawn on the device from (seed, global sample index) as the reference does "
+                                          "(torch.randn on the GPU): informational, NOT the e2e value"},
                "api": f"NaturalInferenceSampler.sample_host_many(pixels={pixels}), double-buffered copy streams: pinned {dts} noise in, " + ("NHWC uint8 out" if pixels else f"{dts} latent out")}
 
     # ---- optional comparator: the reference's own loop structure (oracle restatement: fp64 history, one torch kernel

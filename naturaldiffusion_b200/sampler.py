@@ -100,8 +100,10 @@ class NaturalInferenceSampler:
         off = int(sample_offset) * self.per_sample
         if off != self.elem_offset:
             self.elem_offset = off
-            self._launch_cache.clear()
-            self._launches = self._launch_key = None
+            for launches in self._launch_cache.values():  # prepared descriptors stay valid: only the Philox index moves
+                for row in launches:
+                    for L in row:
+                        L.desc.elem_offset = off
             self._graph = None
 
     # ------------------------------------------------------------------ views
@@ -322,13 +324,16 @@ class NaturalInferenceSampler:
 
 
     @torch.no_grad()
-    def sample_host_many(self, denoiser: Callable, noise_hosts: Sequence[torch.Tensor], out_hosts: Sequence[torch.Tensor], pixels: bool = False):
+    def sample_host_many(self, denoiser: Callable, noise_hosts: Optional[Sequence[torch.Tensor]], out_hosts: Sequence[torch.Tensor],
+                         pixels: bool = False, first_sample: int = 0):
         """Pipelined end-to-end over many batches with HOST buffers (the reference generates 100 batches of 500,
         src/CIFAR10NaturalInference.py:288-309): the H2D copy of batch i+1 and the D2H copy of batch i-1 run on
         their own streams while batch i computes; two device staging buffers per direction.  Returns after
-        enqueueing everything; the caller synchronises (torch.cuda.synchronize or the returned event)."""
-        n = len(noise_hosts)
-        if len(out_hosts) != n:
+        enqueueing everything; the caller synchronises (torch.cuda.synchronize or the returned event).
+        noise_hosts=None: like the reference, draw the noise on the device (in-kernel Philox keyed by the global sample
+        index first_sample + i*B) -- nothing but the results crosses PCIe."""
+        n = len(out_hosts)
+        if noise_hosts is not None and len(noise_hosts) != n:
             raise NiError("need one output buffer per noise batch")
         shape = self.full_shape()
         dev = self.device
@@ -344,19 +349,23 @@ class NaturalInferenceSampler:
         main = torch.cuda.current_stream(dev)
         c_done, d_done = [None] * n, [None] * n
         for i in range(n):
-            nh = noise_hosts[i]
-            if nh.device.type != "cpu" or nh.shape != shape or nh.dtype != self.dtype:
-                raise NiError("noise_hosts[i] must be CPU tensors matching the state shape/dtype")
             nb, ob = st["noise"][i % 2], st["out"][i % 2]
-            with torch.cuda.stream(st["h2d"]):
-                if i >= 2:
-                    st["h2d"].wait_event(c_done[i - 2])      # batch i-2 no longer reads this noise buffer
-                else:
-                    st["h2d"].wait_stream(main)
-                nb.copy_(nh, non_blocking=True)
-                h_done = torch.cuda.Event()
-                h_done.record(st["h2d"])
-            main.wait_event(h_done)
+            if noise_hosts is not None:
+                nh = noise_hosts[i]
+                if nh.device.type != "cpu" or nh.shape != shape or nh.dtype != self.dtype:
+                    raise NiError("noise_hosts[i] must be CPU tensors matching the state shape/dtype")
+                with torch.cuda.stream(st["h2d"]):
+                    if i >= 2:
+                        st["h2d"].wait_event(c_done[i - 2])      # batch i-2 no longer reads this noise buffer
+                    else:
+                        st["h2d"].wait_stream(main)
+                    nb.copy_(nh, non_blocking=True)
+                    h_done = torch.cuda.Event()
+                    h_done.record(st["h2d"])
+                main.wait_event(h_done)
+            else:
+                self.set_sample_offset(first_sample + i * self.batch)
+                nb = None
             if i >= 2:
                 main.wait_event(d_done[i - 2])                # batch i-2's result has left this output buffer
             if pixels:

@@ -408,6 +408,12 @@ def test_host_buffer_paths_match_device_path(weights_dir):
     s.sample_host(den, noises[3], o1, pixels=True)
     torch.cuda.synchronize()
     assert torch.equal(o1, refs[3])
+    # seeded variant: noise drawn on the device, keyed by the global sample index -> equals one big sharded run
+    so = [torch.empty(256, 32, 32, 3, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    s.sample_host_many(den, None, so, pixels=True, first_sample=512)
+    torch.cuda.synchronize()
+    _, big = _c2_sampler(weights_dir, 768, sample_offset=512)
+    assert torch.equal(torch.cat(so), to_pixel_u8(big.sample(den)).cpu())
     _, s2 = _c2_sampler(weights_dir, 256)
     lat = [torch.empty(256, 3, 32, 32).pin_memory() for _ in range(3)]
     s2.sample_host_many(den, noises[:3], lat, pixels=False)
