@@ -670,3 +670,40 @@ def test_sd3_flow_euler_matrix_equals_vanilla_euler():
     assert rel_err(x, ref) < 2e-6
     dense = NaturalInferenceSampler(triple, io_velocity_cfg(sig, 7.0), 3, (16, 16, 16), device=DEV, seed=10, markov=False)
     assert rel_err(dense.sample(den), ref) < 2e-6
+
+
+def test_sampler_chains_rows_longer_than_512_terms():
+    """dense DDPM-300 rows reach 300 + 301 stored terms > NI_MAX_TERMS: the sampler chains two launches per step
+    (accumulate=1); result equals the first-order path and the fused uint8 stage still works on a chained last row"""
+    from naturaldiffusion_b200.generators import ddpm_triple
+    from toy_models import ToyVPDenoiser
+    K, B = 300, 4
+    triple = ddpm_triple(K)
+    c1, c2, _ = ddim_x0_coeffs(K)
+    net = ToyVPDenoiser(3)
+    den = lambda z, k: net(z, triple.node[k, 0], 0)
+    dense = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, None), B, (3, 8, 8), device=DEV, seed=2, markov=False)
+    assert max(dense.plan.launches(k) for k in range(K)) == 2 and dense.kernel_launches_per_trajectory > K
+    n0 = ni.launch_count()
+    xd = dense.sample(den).clone()
+    assert ni.launch_count() - n0 == dense.kernel_launches_per_trajectory + 1
+    fast = NaturalInferenceSampler(triple, io_eps_cfg(c1, c2, None), B, (3, 8, 8), device=DEV, seed=2)
+    assert fast.plan.markov and rel_err(xd, fast.sample(den)) < 1e-5
+    pix = torch.empty(B, 8, 8, 3, dtype=torch.uint8, device=DEV)
+    assert torch.equal(dense.sample(den, pixels_out=pix), to_pixel_u8(xd))
+
+
+def test_cuda_graph_capture_of_a_whole_trajectory(weights_dir):
+    """sampler.capture(): denoiser (torch ops) + K fused steps in one CUDA graph; replays reproduce the eager run and
+    follow a refilled static noise buffer"""
+    den = lambda x, k: torch.tanh(0.7 * x) * (1.0 + 0.01 * k) + 0.1 * x
+    triple, s = _c2_sampler(weights_dir, 128)
+    noise = philox_normal((128, 3, 32, 32), seed=3, tensor_id=0, device=DEV)
+    eager = s.sample(den, noise=noise).clone()
+    s.capture(den, noise=noise)
+    n0 = ni.launch_count()
+    assert torch.equal(s.replay(), eager) and ni.launch_count() == n0  # replays launch from the graph, not through the ABI
+    noise.copy_(philox_normal((128, 3, 32, 32), seed=4, tensor_id=0, device=DEV))
+    got = s.replay().clone()
+    s._graph = None
+    assert torch.equal(got, s.sample(den, noise=noise)) and not torch.equal(got, eager)
