@@ -14,9 +14,8 @@ tensors; there is no CPU fallback.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
-import numpy as np
 import torch
 
 from ._lib import NiError

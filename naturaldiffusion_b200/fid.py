@@ -9,8 +9,6 @@ Frechet distance are then a host-side O(d^3) step exactly as in the reference.  
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 import torch
 

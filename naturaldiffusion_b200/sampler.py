@@ -25,7 +25,7 @@ import torch
 from . import _lib
 from ._lib import NI_BF16, NI_MAX_TERMS, NiError
 from .coeffs import CoeffTriple, StepPlan, build_plan
-from .ops import DTYPE_CODE, StepLaunch, philox_normal, stream_ptr, to_pixel_u8
+from .ops import DTYPE_CODE, StepLaunch, philox_normal, stream_ptr
 
 
 class NaturalInferenceSampler:

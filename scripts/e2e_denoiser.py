@@ -9,7 +9,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -90,7 +89,6 @@ def main():
                "ours_ms_per_trajectory": ms_ours, "ours_samples_per_s": world * args.batch / (ms_ours * 1e-3),
                "denoiser_only_ms": ms_model, "update_share_ours": max(0.0, 1 - ms_model / ms_ours)}
         if world == 1:
-            noise = ni.ops.philox_normal(s.full_shape(), seed=888, tensor_id=0, device=dev) if hasattr(ni, "ops") else None
             from naturaldiffusion_b200.ops import philox_normal
             noise = philox_normal(s.full_shape(), seed=888, tensor_id=0, device=dev)
             plain = (lambda x, labels: model(x, labels)) if ac is None else (lambda x, labels: torch.autocast("cuda", dtype=ac)(model)(x, labels).float())

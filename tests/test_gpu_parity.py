@@ -476,7 +476,6 @@ def test_c1_ddim10_ncsnpp_ni_equals_original_ddim():
     """config C1: DDIM 10 steps, NCSN++ (61.8 M params, random init, last conv re-initialised), batch 64 x 3x32x32.
     The reference's consistency check (src/ValidateNaturalInference.py:375-391): the ORIGINAL DDIM loop and Natural
     Inference with the matching matrix give the same samples -- here with the NI side on the fused CUDA path."""
-    from naturaldiffusion_b200.adapters import ncsnpp_denoiser
     from naturaldiffusion_b200.denoisers import NCSNppVP
     from naturaldiffusion_b200.generators import ddim_triple
     K, B = 10, 64
