@@ -798,6 +798,8 @@ template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cuda
     if (stages < 2) return NI_OK;
     if (nw > stages) nw = stages;      // a consumer warp without a stage of its own would only wait
     stages -= stages % nw;             // stage of tile `it` is it % stages; keep it aligned with the warp owning it
+                                       // (an unaligned ring -- more stages than a multiple of nw -- faulted on the device
+                                       //  in round 1 and is not used)
     const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TMA_TILE_BYTES;
     static thread_local int attr_dev = -1; // the opt-in is per device
     int dev = 0;

@@ -31,6 +31,11 @@ if "--tma2" in sys.argv:
                 RUNS.append((cfg, ["--variant", "2", "--opt", f"tma_warps={w}", "--opt", f"tma_ctas_per_sm={c}"]))
         RUNS.append((cfg, ["--variant", "2", "--opt", "tma_warps=16", "--opt", "tma_ctas_per_sm=2", "--opt", "tma_smem_kb=226"]))
         RUNS.append((cfg, ["--variant", "2", "--opt", "tma_warps=8", "--opt", "tma_ctas_per_sm=3"]))
+if "--tma3" in sys.argv:
+    RUNS = [("c2", ["--variant", "1"]), ("c3", ["--variant", "1"])]
+    for cfg in ("c2", "c3"):
+        for w, c in ((6, 1), (8, 1), (12, 1), (4, 2), (6, 2), (7, 2), (4, 3)):
+            RUNS.append((cfg, ["--variant", "2", "--opt", f"tma_warps={w}", "--opt", f"tma_ctas_per_sm={c}"]))
 if "--pdl" in sys.argv:
     RUNS = [(c, ["--opt", f"pdl={v}"] + e) for c, e in (("c2", []), ("c3", []), ("c4", []), ("c5", []), ("c5", ["--batch", "4"])) for v in (0, 1)]
 if "--ldg-only" in sys.argv:
@@ -43,7 +48,11 @@ for lib in libs:
             env["NI_B200_LIB"] = os.path.abspath(lib)
         steps = {"c2": "1500", "c3": "300", "c4": "50", "c5": "300"}.get(cfg, "100")
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", cfg, "--steps", steps, "--warmup", "20", "--no-cpu-baseline", "--no-e2e"] + extra
-        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=120)
+        except subprocess.TimeoutExpired:
+            print(f"{lib} {cfg} {extra} TIMEOUT (120 s) -- aborting the sweep", flush=True)
+            break
         try:
             j = json.loads(r.stdout.strip().splitlines()[-1])
             line = f"{os.path.basename(lib) if lib else 'default':28s} {cfg} {' '.join(extra):42s} ms/traj={j['ms_per_step']:.4f} GB/s={j['roofline']['achieved']:.0f} frac={j['roofline']['frac']:.3f} sm_mhz={j['clocks']['sm_mhz']}"
