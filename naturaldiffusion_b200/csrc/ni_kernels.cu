@@ -797,9 +797,11 @@ template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cuda
     if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
     if (stages < 2) return NI_OK;
     if (nw > stages) nw = stages;      // a consumer warp without a stage of its own would only wait
-    stages -= stages % nw;             // stage of tile `it` is it % stages; keep it aligned with the warp owning it
-                                       // (an unaligned ring -- more stages than a multiple of nw -- faulted on the device
-                                       //  in round 1 and is not used)
+    // Stage of tile `it` is it % stages, its consumer is warp it % nw.  stages must be a multiple of nw so that every
+    // barrier has ONE waiter walking its phases in order: mbarrier parity waits only tell the current phase from the
+    // previous one, and with an unaligned ring a warp running ahead would wait on a phase two steps in the future, get
+    // the stale parity of the preceding phase, read an unfilled stage and release it early (observed: launch failure).
+    stages -= stages % nw;
     const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TMA_TILE_BYTES;
     static thread_local int attr_dev = -1; // the opt-in is per device
     int dev = 0;
