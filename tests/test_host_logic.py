@@ -111,6 +111,46 @@ def test_plan_never_reads_a_recycled_slot(weights_dir):
             assert np.array_equal(row, np.where(t.A[k] != 0, t.A[k], 0.0))
 
 
+def test_ring_plan_on_random_sparse_matrices():
+    """liveness / slot allocation under arbitrary zero patterns: simulate the ring on the host and check that every read
+    finds its column resident, that slots are never shared by two live columns, and that the slot count equals the
+    peak number of simultaneously live columns (the allocation is optimal for interval graphs)"""
+    for seed in range(60):
+        rng = np.random.default_rng(seed)
+        K = int(rng.integers(1, 25))
+        A = np.tril(rng.standard_normal((K, K))) * (rng.random((K, K)) < rng.uniform(0.05, 1.0))
+        A[np.arange(K), np.arange(K)] = 1.0
+        B = np.zeros((K, K + 1))
+        B[:, 0] = rng.standard_normal(K) * (rng.random(K) < 0.7)
+        if seed % 2:
+            for k in range(K):
+                B[k, 1:k + 2] = rng.standard_normal(k + 1) * (rng.random(k + 1) < rng.uniform(0.1, 0.9))
+        t = CoeffTriple(A, B, np.zeros((K + 1, 3)))
+        p = build_plan(t)
+        x0_res, eps_res, peak_x0, peak_eps = {}, {}, 0, 0
+        for k, s in enumerate(p.steps):
+            for j, c in s.hist:
+                assert x0_res.get(p.x0_slot_of[j]) == j and c == A[k, j]
+            for j, c in s.eps:
+                assert c == B[k, j]
+                if j > 0:
+                    assert eps_res.get(p.eps_slot_of[j]) == j
+            if s.keep_x0:
+                assert x0_res.get(s.x0_slot) is None or max(kk for kk in range(K) if A[kk, x0_res[s.x0_slot]] != 0) < k
+                x0_res[s.x0_slot] = k
+            if s.keep_fresh:
+                eps_res[s.fresh_slot] = k + 1
+            # a slot is busy at step k if its column is still READ at step k or later (no slot is recycled inside the
+            # kernel that reads it), plus the column produced at step k if a later row needs it
+            live_x0 = sum(1 for j in range(k) if any(A[kk, j] != 0 for kk in range(k, K))) + int(any(A[kk, k] != 0 for kk in range(k + 1, K)))
+            live_eps = sum(1 for j in range(1, k + 1) if any(B[kk, j] != 0 for kk in range(k, K))) + int(any(B[kk, k + 1] != 0 for kk in range(k + 1, K)))
+            peak_x0, peak_eps = max(peak_x0, live_x0), max(peak_eps, live_eps)
+            assert {j for j, _ in s.hist} == {j for j in range(k) if A[k, j] != 0}
+            assert {j for j, _ in s.eps} == {j for j in range(k + 1) if B[k, j] != 0}
+            assert (s.fresh is not None and s.fresh != 0.0) == (B[k, k + 1] != 0)
+        assert p.n_x0_slots == peak_x0 and p.n_eps_slots == peak_eps, (seed, p.n_x0_slots, peak_x0, p.n_eps_slots, peak_eps)
+
+
 def test_algorithmic_units_formula(weights_dir):
     """bytes(k) = s*N*[m + 1 + write_x0 + (nnzA-1) + nnzB_stored + w_eps + 1]"""
     t = CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz"))
