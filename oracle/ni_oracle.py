@@ -19,7 +19,6 @@ and against the shipped coefficient matrices (44 under results/).  Parity is the
 """
 from __future__ import annotations
 
-import io
 from typing import Callable, Sequence
 
 import numpy as np
@@ -415,12 +414,6 @@ def to_pixel_u8(x):
     y = (x + 1.0) / 2.0
     y = y.permute(0, 2, 3, 1).contiguous().numpy()
     return np.clip(y * 255, 0, 255).astype(np.uint8)
-
-
-def npz_bytes(**arrays):
-    buf = io.BytesIO()
-    np.savez(buf, **arrays)
-    return buf.getvalue()
 
 
 # --------------------------------------------------------------------------------------

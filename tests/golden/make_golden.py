@@ -163,6 +163,19 @@ def gen_sd3():
     np.savez_compressed(os.path.join(HERE, "sd3_loop.npz"), **out)
 
 
+def gen_weights():
+    """The shipped inputs of the hot path (weights/*.npz, weights/*.csv): re-saved array by array / line by line so the
+    fixtures carry exactly the reference's numbers (positional npz order kept: xstart, epsilon, node)."""
+    out_dir = os.path.join(HERE, "reference_weights")
+    os.makedirs(out_dir, exist_ok=True)
+    for f in sorted(glob.glob(os.path.join(REF, "weights", "*.npz"))):
+        with np.load(f) as z:
+            np.savez(os.path.join(out_dir, os.path.basename(f)), **{k: z[k] for k in z.files})
+    for f in sorted(glob.glob(os.path.join(REF, "weights", "*.csv"))):
+        with open(f) as src, open(os.path.join(out_dir, os.path.basename(f)), "w") as dst:
+            dst.write(src.read())
+
+
 def gen_matrices():
     """The shipped coefficient matrices (results/*/*.npz): golden outputs of the reference's generators.
     K <= 201 are stored whole; the two K=500 files as float64 row/column digests to keep the repo small."""
@@ -178,6 +191,7 @@ def gen_matrices():
 
 
 if __name__ == "__main__":
+    gen_weights()
     gen_cifar()
     gen_validate()
     gen_sd3()
