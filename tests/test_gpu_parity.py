@@ -706,3 +706,24 @@ def test_cuda_graph_capture_of_a_whole_trajectory(weights_dir):
     got = s.replay().clone()
     s._graph = None
     assert torch.equal(got, s.sample(den, noise=noise)) and not torch.equal(got, eager)
+
+
+def test_presets_build_the_three_reference_configurations(weights_dir):
+    """presets.cifar / dit / sd3: the loop-level drop-in in one line per reference script"""
+    from naturaldiffusion_b200 import presets
+    from naturaldiffusion_b200.denoisers import DiT, MMDiT, NCSNppVP
+    from naturaldiffusion_b200.generators import ddim_triple
+    torch.manual_seed(0)
+    s, wrap = presets.cifar(os.path.join(weights_dir, "step_5_weight_00.npz"), batch=4)
+    net = NCSNppVP(nf=32, num_res_blocks=1).reinit_output().to(DEV).eval()
+    pix = s.sample(wrap(net), pixels_out=torch.empty(4, 32, 32, 3, dtype=torch.uint8, device=DEV))
+    assert pix.shape == (4, 32, 32, 3) and s.plan.n_x0_slots == 2
+    s, wrap = presets.dit(ddim_triple(10), batch=2, vae_scale=True)
+    dit_net = DiT(dim=64, depth=1, heads=4).reinit_output().to(DEV).eval()
+    z = s.sample(wrap(dit_net, torch.tensor([1, 2], device=DEV)))
+    assert z.shape == (2, 4, 32, 32) and s.plan.markov and abs(s.final_scale - 1 / 0.18215) < 1e-12 and torch.isfinite(z).all()
+    s, wrap = presets.sd3(os.path.join(weights_dir, "sd3_step_28_weight_sharp.csv"), batch=1, latent=(16, 16, 16))
+    mm = MMDiT(dim=64, depth=1, heads=4, ctx_dim=8, pooled_dim=8, max_grid=16).to(DEV).half().eval()
+    c, p = torch.randn(1, 3, 8, device=DEV).half(), torch.randn(1, 8, device=DEV).half()
+    out = s.sample(wrap(mm, c, p, -c, -p))
+    assert out.dtype == torch.float16 and s.plan.n_x0_slots == 14 and torch.isfinite(out).all()
