@@ -34,7 +34,16 @@ def _row_form(row, seq: Sequence[torch.Tensor]) -> torch.Tensor:
     return weighted_sum_tensors([coeffs[i] for i in keep], [seq[i] for i in keep], out_dtype=torch.float32)
 
 
-_sd3_memo = {"key": None, "val": None}
+_sd3_memo = {"refs": None, "versions": None, "w": None, "val": None}
+
+
+def _memo_hit(seq, w):
+    """the memoised call is reused only for the very same live tensor objects, unmodified since, and the same weights
+    (data pointers alone could alias a freed tensor of an earlier run)"""
+    refs = _sd3_memo["refs"]
+    if refs is None or len(refs) != len(seq) or _sd3_memo["w"] != w:
+        return False
+    return all(r() is t and v == t._version for r, v, t in zip(refs, _sd3_memo["versions"], seq))
 
 
 def _sd3_form(seq: Sequence[torch.Tensor], weights=None, memoise: bool = True) -> torch.Tensor:
@@ -42,12 +51,12 @@ def _sd3_form(seq: Sequence[torch.Tensor], weights=None, memoise: bool = True) -
     normalised by its sum; result in the tensors' dtype (fp32 accumulate instead of the reference's fp16).
     The SD3 loop calls it twice with identical arguments (:221 then :207 of the next step); the second call
     returns the memoised tensor."""
+    import weakref
     n = len(seq)
     if n == 0:
         raise NiError("weighted_sum of an empty sequence")
-    w = [1.0] * n if weights is None else [float(weights[n - 1][i]) for i in range(n)]
-    key = (n, tuple(t.data_ptr() for t in seq), tuple(w))
-    if memoise and _sd3_memo["key"] == key:
+    w = tuple([1.0] * n if weights is None else [float(weights[n - 1][i]) for i in range(n)])
+    if memoise and _memo_hit(seq, w):
         return _sd3_memo["val"]
     tot = float(sum(w))
     keep = [i for i in range(n) if w[i] != 0.0]
@@ -56,7 +65,7 @@ def _sd3_form(seq: Sequence[torch.Tensor], weights=None, memoise: bool = True) -
     else:
         out = weighted_sum_tensors([w[i] for i in keep], [seq[i] for i in keep], scale=1.0 / tot)
     if memoise:
-        _sd3_memo["key"], _sd3_memo["val"] = key, out
+        _sd3_memo.update(refs=[weakref.ref(t) for t in seq], versions=[t._version for t in seq], w=w, val=out)
     return out
 
 

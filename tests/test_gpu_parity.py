@@ -325,6 +325,11 @@ def test_dropin_functions(golden_dir, weights_dir):
     r1 = dropin.weighted_sum(seq7, W)
     assert rel_err(r1, O.sd3_weighted_sum([t.cpu() for t in seq7], W)) < 1e-6
     assert dropin.weighted_sum(seq7, W) is r1
+    seq7[3].add_(1.0)  # an in-place change, or new tensors that happen to reuse the addresses, must not hit the memo
+    r2 = dropin.weighted_sum(seq7, W)
+    assert r2 is not r1 and rel_err(r2, O.sd3_weighted_sum([t.cpu() for t in seq7], W)) < 1e-6
+    fresh = [t.clone() for t in seq7]
+    assert dropin.weighted_sum(fresh, W) is not r2
 
 
 def test_dropin_data_fn_and_install():
