@@ -81,13 +81,23 @@ _scalar_cache = {}
 
 
 def _as_float(w) -> float:
+    """host value of a weight; device scalars (the SD3 script carries sigma differences as 0-d CUDA tensors) cost one
+    sync the first time they are seen and are then cached by OBJECT identity (weak reference + version), never by
+    address: a later tensor reusing the memory of a freed one must not inherit its value."""
     if isinstance(w, torch.Tensor):
-        k = (w.data_ptr(), w._version)
-        if k not in _scalar_cache:
+        import weakref
+        k = id(w)
+        hit = _scalar_cache.get(k)
+        if hit is not None and hit[0]() is w and hit[1] == w._version:
+            return hit[2]
+        if len(_scalar_cache) > 4096:
+            for key in [key for key, (r, _, _) in _scalar_cache.items() if r() is None]:
+                del _scalar_cache[key]
             if len(_scalar_cache) > 4096:
                 _scalar_cache.clear()
-            _scalar_cache[k] = float(w.item())  # one sync per NEW device scalar (the reference prints .item() per step anyway)
-        return _scalar_cache[k]
+        val = float(w.item())  # (the reference prints .item() of these every step anyway)
+        _scalar_cache[k] = (weakref.ref(w), w._version, val)
+        return val
     return float(w)
 
 
