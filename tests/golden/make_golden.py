@@ -176,6 +176,29 @@ def gen_weights():
             dst.write(src.read())
 
 
+def gen_config_matrices():
+    """The two matrices BASELINE's configs need but the reference does not ship: ddim_010 (C1) and ddpm_250 (C4), produced by
+    the reference's OWN generators (src/AnalyzeDDPMDDIM.py `ddim_analyze_coeff`, `ddpm_analyze_coeff`) with their file
+    writer intercepted (the reference tree is read-only)."""
+    import contextlib
+    import io
+    mod = ref_loader.analyze_ddpm_ddim_module()
+    got = {}
+
+    def capture(A, B, node, out_dir, prefix):
+        got["%s_%03d" % (prefix, A.shape[0])] = (A.copy(), B.copy(), node.copy())
+
+    mod.save_coeff_matrix = capture
+    with contextlib.redirect_stdout(io.StringIO()):
+        mod.ddim_analyze_coeff(10)
+        mod.ddpm_analyze_coeff(250)
+        mod.ddpm_analyze_coeff(10)
+    out = {}
+    for key, (A, B, node) in got.items():
+        out[key + "/A"], out[key + "/B"], out[key + "/node"] = A, B, node
+    np.savez_compressed(os.path.join(HERE, "config_matrices.npz"), **out)
+
+
 def gen_matrices():
     """The shipped coefficient matrices (results/*/*.npz): golden outputs of the reference's generators.
     K <= 201 are stored whole; the two K=500 files as float64 row/column digests to keep the repo small."""
@@ -196,5 +219,6 @@ if __name__ == "__main__":
     gen_validate()
     gen_sd3()
     gen_matrices()
+    gen_config_matrices()
     for f in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
         print(os.path.basename(f), os.path.getsize(f))

@@ -317,6 +317,19 @@ def test_every_shipped_matrix_is_reproduced(golden_dir):
     assert done == 44
 
 
+def test_config_matrices_match_the_reference_generators(golden_dir):
+    """ddim_010 (BASELINE config C1) and ddpm_250 (C4) are not shipped by the reference; tests/golden/config_matrices.npz
+    holds what the reference's OWN generators output for them (make_golden.py::gen_config_matrices).  Both the product
+    generators and the oracle's restatement reproduce them."""
+    z = np.load(os.path.join(golden_dir, "config_matrices.npz"))
+    for key, fn, ofn, K in (("ddim_010", generators.ddim_triple, O.ddim_triple, 10), ("ddpm_250", generators.ddpm_triple, O.ddpm_triple, 250),
+                            ("ddpm_010", generators.ddpm_triple, O.ddpm_triple, 10)):
+        t, (A, B, node) = fn(K), ofn(K)
+        for got_A, got_B, got_node in ((t.A, t.B, t.node), (A, B, node)):
+            assert np.abs(got_A - z[key + "/A"]).max() < 1e-15 and np.abs(got_B - z[key + "/B"]).max() < 1e-15
+            assert np.array_equal(got_node, z[key + "/node"])
+
+
 def test_schedule_helpers():
     assert spaced_timesteps(1000, 10) == [0, 111, 222, 333, 444, 555, 666, 777, 888, 999]
     assert spaced_timesteps(1000, 10) == O.spaced_steps(1000, 10)
