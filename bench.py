@@ -428,6 +428,7 @@ def run_ours(args, rank, world, local_rank):
                                f"null denoiser ({m} pre-generated N(0,1) model output(s) of {cout} channels re-read from HBM each step)",
                    "markov_fast_path": bool(sampler.plan.markov),
                    "shape": [batch] + list(shape), "eps0": args.eps0, "numa_bound_cpus": numa_cpus, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
+                   "load_flavour": "auto per launch: ld.global.L1::no_allocate when the bytes it writes fit in 0.6 of the L2 and are >= 1/16 of its traffic, else plain ld.global (override: --opt load_policy=1|2)",
                    "l2": f"inputs larger than L2: per-trajectory working set {(sampler.state_bytes() + sum(o.numel() for o in outs) * esize) / 1e6:.0f} MB vs 126 MB L2",
                    "state_bytes": sampler.state_bytes()},
         "clocks": clk,

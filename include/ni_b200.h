@@ -112,7 +112,10 @@ int64_t ni_launch_count(void);
 
 /* Tuning knobs, process-wide: "variant" 0 auto | 1 direct-load kernel | 2 TMA-staged kernel when eligible;
  * "tma_max_stages" 2..32; "tma_warps" 1..16; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4; "pdl" 0|1 (programmatic
- * dependent launch of the direct-load step kernel, default 1).  Results do not depend on them. */
+ * dependent launch of the direct-load step kernel, default 1); "load_policy" 0 auto | 1 L2-friendly loads
+ * (ld.global.L1::no_allocate) | 2 streaming loads (plain ld.global) -- auto picks L2-friendly loads when what the
+ * launch writes fits in 0.6 of the L2 and is >= 1/16 of its traffic, streaming otherwise (measured:
+ * profiles/r01_policy_sweep.txt).  Results do not depend on them. */
 int ni_set_option(const char *name, int value);
 
 int ni_step(const NiStepDesc *desc_host, void *stream);

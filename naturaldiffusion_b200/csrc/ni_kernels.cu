@@ -23,8 +23,18 @@
 #include <cstring>
 #include <type_traits>
 
+// 128-bit load flavours (SASS): 0 plain ld.global (LDG.E.128), 1 ld.global.L1::no_allocate (LDG.E.NA.128), 2 ld.global.cs
+// (evict-first), 4 plain + L2::256B prefetch.  Measured on B200 (profiles/r01_policy_sweep.txt): when a launch streams far
+// more than the 126 MB L2 can hold (C2, C3) plain loads are 1.2% / 3.8% faster than NA loads -- NA-loaded lines are the
+// first to leave L2, so the dirty lines of the stores pile up and drain in bursts; evict-first STORES with NA loads recover
+// the same 3.4% on C3 -- while on launches whose tensors fit in L2 (SD3 first-order path, 33 MB tensors) NA loads are 11%
+// faster because the x_{k+1} just written survives until the next step reads it.  The step kernel is therefore built in
+// both flavours and the host picks per launch (see launch_streams); everything else uses NI_LOAD_POLICY.
 #ifndef NI_LOAD_POLICY
-#define NI_LOAD_POLICY 1 /* 0 plain ld.global, 1 ld.global.L1::no_allocate, 2 ld.global.cs (evict-first) */
+#define NI_LOAD_POLICY 1
+#endif
+#ifndef NI_STREAM_LOAD_POLICY
+#define NI_STREAM_LOAD_POLICY 0 /* flavour of the step kernel's loads when the launch footprint is >> L2 */
 #endif
 #ifndef NI_STORE_POLICY
 #define NI_STORE_POLICY 0 /* 0 plain st.global, 1 st.global.cs */
@@ -53,6 +63,7 @@ std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
 std::atomic<int> g_tma_ctas_per_sm{2};
 std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernel
+std::atomic<int> g_load_policy{0};   // step-kernel load flavour: 0 by launch footprint vs L2, 1 always L2-friendly (NA), 2 always streaming
 
 int fail(int code, const char *fmt, ...)
 {
@@ -66,16 +77,13 @@ int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------------
 // raw vector loads / stores with cache policy
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ld128(const void *p)
+template <int POL> __device__ __forceinline__ uint4 ld128_pol(const void *p)
 {
     uint4 r;
-#if NI_LOAD_POLICY == 1
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#elif NI_LOAD_POLICY == 2
-    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#else
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#endif
+    if constexpr (POL == 1) asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if constexpr (POL == 2) asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if constexpr (POL == 4) asm volatile("ld.global.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint2 ld64(const void *p)
@@ -113,15 +121,15 @@ template <typename T, int VEC> struct Raw {
     uint32_t w[WORDS];
 };
 
-template <typename T, int VEC> __device__ __forceinline__ Raw<T, VEC> load_raw(const T *p)
+template <typename T, int VEC, int POL = NI_LOAD_POLICY> __device__ __forceinline__ Raw<T, VEC> load_raw(const T *p)
 {
     Raw<T, VEC> r;
     constexpr int BYTES = Raw<T, VEC>::BYTES;
     if constexpr (BYTES == 32) {
-        uint4 a = ld128(p), b = ld128(reinterpret_cast<const char *>(p) + 16);
+        uint4 a = ld128_pol<POL>(p), b = ld128_pol<POL>(reinterpret_cast<const char *>(p) + 16);
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
     } else if constexpr (BYTES == 16) {
-        uint4 a = ld128(p);
+        uint4 a = ld128_pol<POL>(p);
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
     } else if constexpr (BYTES == 8) {
         uint2 a = ld64(p);
@@ -412,9 +420,11 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int6
 }
 
 // ---- variant 1: direct 128-bit global loads, one vector per thread ---------------------------------
-template <typename T, typename TO, int VEC, int CAP>
+// STREAM selects the load flavour (cache hints only, same arithmetic): true when the launch footprint is >> L2
+template <typename T, typename TO, int VEC, int CAP, bool STREAM>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
+    constexpr int POL = STREAM ? NI_STREAM_LOAD_POLICY : NI_LOAD_POLICY;
     // PDL: let the next grid start launching now; do not touch global memory before the previous grid is complete
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
@@ -433,14 +443,14 @@ __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const 
     if (has_x0) {
         int64_t eo = e;
         if (s.out_strided) eo = sample * s.out_sample_stride + (e - sample * s.per_sample);
-        ro0 = load_raw<TO, VEC>(static_cast<const TO *>(s.out0) + eo);
-        if (has_o1) ro1 = load_raw<TO, VEC>(static_cast<const TO *>(s.out1) + eo);
-        if (has_x) rx = load_raw<T, VEC>(static_cast<const T *>(s.x_in) + e);
+        ro0 = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out0) + eo);
+        if (has_o1) ro1 = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out1) + eo);
+        if (has_x) rx = load_raw<T, VEC, POL>(static_cast<const T *>(s.x_in) + e);
     }
 
     float acc[VEC];
     if (s.accumulate) {
-        unpack<T, VEC>(load_raw<T, VEC>(static_cast<const T *>(s.x_next) + e), acc);
+        unpack<T, VEC>(load_raw<T, VEC, POL>(static_cast<const T *>(s.x_next) + e), acc);
     } else {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
@@ -452,7 +462,7 @@ __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const 
 #define NI_TERM_BATCH(NB)                                                                                                     \
     for (; t + NB <= n; t += NB) {                                                                                            \
         Raw<T, VEC> rr[NB];                                                                                                   \
-        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC>(static_cast<const T *>(tab.ptr[t + j]) + e);  \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC, POL>(static_cast<const T *>(tab.ptr[t + j]) + e); \
         _Pragma("unroll") for (int j = 0; j < NB; ++j) fma_term<T, VEC>(acc, rr[j], tab.c[t + j]);                            \
     }
 #if NI_TERM_BATCH_MAX >= 8
@@ -759,34 +769,71 @@ template <typename Kern, typename... Args> void launch_pdl(Kern kern, unsigned b
     cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-template <typename T, typename TO, int VEC>
-int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
+struct DevInfo { int sms; int64_t l2_bytes; };
+
+const DevInfo &dev_info()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo info = {148, 126 << 20};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev) {
+        int sms = 0, l2 = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        info.sms = sms > 0 ? sms : 148;
+        info.l2_bytes = l2 > 0 ? l2 : (126 << 20);
+        cached_dev = dev;
+    }
+    return info;
+}
+
+// Which load flavour a launch gets.  What the L2 can usefully keep between steps is what this launch WRITES (x_{k+1},
+// x0_k, kept noise: the next step and the denoiser read them first).  L2-friendly loads keep those lines resident (the
+// streamed history leaves first), which pays when they fit -- measured: up to ~0.6 of the L2, 67 MB written per launch
+// on the SD3 shapes (+2..11%) but not C2's 100 MB (-1.2%) -- and when they are a visible share of the traffic (DDPM-250
+// dense rows write 3 of ~250 tensors: streaming +1.7%).  Everything else streams.  profiles/r01_policy_sweep.txt.
+bool launch_streams(const StepArgs &a, const NiStepDesc *d, int elem_size, int out_elem_size)
+{
+    const int pol = g_load_policy.load(std::memory_order_relaxed);
+    if (pol != 0) return pol == 2;
+    int64_t n_written = (a.x0_dst != nullptr ? 1 : 0) + (a.x_next != nullptr ? 1 : 0);
+    for (int g = 0; g < d->n_gen; ++g) n_written += d->gen_dst[g] != nullptr ? 1 : 0;
+    int64_t written = n_written * d->numel * elem_size;
+    if (a.x_next_lp != nullptr) written += d->numel * 2;
+    if (a.pixels != nullptr) written += d->numel;
+    int64_t read = (int64_t)(d->n_terms + (d->accumulate ? 1 : 0) + (a.x_in != nullptr ? 1 : 0)) * d->numel * elem_size;
+    if (d->has_x0) read += (int64_t)(1 + (d->out1 != nullptr ? 1 : 0)) * d->numel * out_elem_size;
+    const int64_t l2 = dev_info().l2_bytes;
+    return 5 * written > 3 * l2 || 16 * written < read + written;
+}
+
+template <typename T, typename TO, int VEC, bool STREAM>
+int launch_step_pol(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
 {
     const unsigned blocks = (unsigned)((a.nvec + NI_BLOCK - 1) / NI_BLOCK);
     if (d->n_terms <= 32) {
         TermTable<32> tab;
         memset(&tab, 0, sizeof(tab));
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        launch_pdl(ni_step_kernel<T, TO, VEC, 32>, blocks, st, a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, 32, STREAM>, blocks, st, a, tab);
     } else {
         static thread_local TermTable<NI_MAX_TERMS> tab;
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        launch_pdl(ni_step_kernel<T, TO, VEC, NI_MAX_TERMS>, blocks, st, a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, NI_MAX_TERMS, STREAM>, blocks, st, a, tab);
     }
     return check_launch("ni_step launch");
 }
 
-int sm_count()
+template <typename T, typename TO, int VEC>
+int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
 {
-    static thread_local int cached_dev = -1, cached = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-        cached_dev = dev;
+    if constexpr (VEC > 1) { // the scalar (misaligned / ragged) path is not a bandwidth path: one flavour
+        if (launch_streams(a, d, (int)sizeof(T), (int)sizeof(TO))) return launch_step_pol<T, TO, VEC, true>(a, d, st);
     }
-    return cached > 0 ? cached : 148;
+    return launch_step_pol<T, TO, VEC, false>(a, d, st);
 }
+
+int sm_count() { return dev_info().sms; }
 
 // TMA variant: eligible when the row fits one shared-memory stage set and tiles map 1:1 onto sources
 template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cudaStream_t st, bool *used)
@@ -878,6 +925,7 @@ int ni_set_option(const char *name, int value)
     if (!strcmp(name, "tma_warps")) { if (value < 1 || value > TMA_MAX_WARPS) return fail(NI_ERR_INVALID, "tma_warps must be 1..%d", TMA_MAX_WARPS); g_tma_warps = value; return NI_OK; }
     if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NI_OK; }
+    if (!strcmp(name, "load_policy")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "load_policy must be 0..2"); g_load_policy = value; return NI_OK; }
     if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
     return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);
 }

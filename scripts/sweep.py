@@ -38,15 +38,25 @@ if "--tma3" in sys.argv:
             RUNS.append((cfg, ["--variant", "2", "--opt", f"tma_warps={w}", "--opt", f"tma_ctas_per_sm={c}"]))
 if "--pdl" in sys.argv:
     RUNS = [(c, ["--opt", f"pdl={v}"] + e) for c, e in (("c2", []), ("c3", []), ("c4", []), ("c5", []), ("c5", ["--batch", "4"])) for v in (0, 1)]
+if "--policy" in sys.argv:  # step-kernel load flavour forced L2-friendly (1) / streaming (2) / auto (0) on every shape
+    shapes = [("c2", []), ("c3", []), ("c4", ["--markov", "0"]), ("c4", []), ("c5", []), ("c5", ["--markov", "0"]), ("c5s", []),
+              ("c5", ["--batch", "256", "--markov", "0"])]
+    RUNS = [(c, e + ["--opt", f"load_policy={v}"]) for c, e in shapes for v in (1, 2, 0)]
 if "--ldg-only" in sys.argv:
     RUNS = [("c2", ["--variant", "1"]), ("c3", ["--variant", "1"])]
+if "--cfgs" in sys.argv:  # --cfgs c2,c3,c5: the direct-load kernel on the named configs
+    RUNS = [(c, ["--variant", "1"]) for c in sys.argv[sys.argv.index("--cfgs") + 1].split(",")]
 out = []
 for lib in libs:
     for cfg, extra in RUNS:
         env = dict(os.environ)
         if lib:
             env["NI_B200_LIB"] = os.path.abspath(lib)
-        steps = {"c2": "1500", "c3": "300", "c4": "50", "c5": "300"}.get(cfg, "100")
+        steps = {"c2": "1500", "c3": "300", "c4": "50", "c5": "300", "c5s": "300"}.get(cfg, "100")
+        if cfg == "c4" and "0" in extra[:2]:
+            steps = "4"   # dense DDPM-250 rows: 150 ms per trajectory
+        if "256" in extra:
+            steps = "50"
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--config", cfg, "--steps", steps, "--warmup", "20", "--no-cpu-baseline", "--no-e2e"] + extra
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=120)

@@ -222,6 +222,39 @@ def test_tma_variant_is_bit_identical_to_direct_loads(dt, shape, cout, ncond):
     assert torch.allclose(got["sumsq"], ref["sumsq"], rtol=1e-5)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_load_flavours_are_bit_identical(dt, weights_dir):
+    """the streaming (plain ld.global) and the L2-friendly (L1::no_allocate) builds of the step kernel differ in cache
+    hints only; `auto` picks by the launch footprint vs the L2 size, so small and large launches are both exercised"""
+    from naturaldiffusion_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dt).to(DEV)
+    shape = (6, 3, 32, 32)
+    kw = dict(x_in=mk(*shape), outs=[mk(*shape), mk(*shape)], a=0.9, b=[-0.4, 0.25], c_x0=0.7, c_xin=0.05,
+              terms=[(0.2 * (-1) ** i, mk(*shape)) for i in range(11)], gens=[(0.3, 2)], seed=4, keep_gen=[True], want_sumsq=True)
+    res = {}
+    try:
+        for pol in (1, 2, 0):
+            _lib.set_option("load_policy", pol)
+            res[pol] = fused_step(**kw)
+        with pytest.raises(ni.NiError):
+            _lib.set_option("load_policy", 3)
+        # a whole C2-sized trajectory (launch footprints 200-400 MB: streaming under `auto`) against the L2-friendly build
+        triple = CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz"))
+        s = NaturalInferenceSampler(triple, io_score_vp(triple.node), 4096, (3, 32, 32), device=DEV, seed=888)
+        den = lambda x, k: torch.tanh(x) * (1 + 0.01 * k)
+        _lib.set_option("load_policy", 0)
+        auto = s.sample(den).clone()
+        _lib.set_option("load_policy", 1)
+        assert torch.equal(s.sample(den), auto)
+    finally:
+        _lib.set_option("load_policy", 0)
+    for pol in (2, 0):
+        for key in ("x_next", "x0"):
+            assert torch.equal(res[pol][key], res[1][key]), (pol, key)
+        assert torch.equal(res[pol]["gen"][0], res[1]["gen"][0])
+
+
 def test_error_paths_are_loud():
     with pytest.raises(ni.NiError):
         weighted_sum_tensors([1.0], [torch.zeros(4)])  # CPU tensor: no fallback
