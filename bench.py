@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cold", action="store_true", help="run the cold-L2 per-launch check on c4/c5 too (default: c2/c3 only)")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold-L2 per-launch check (keeps profiler launch lists to the timed region)")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--eager-comparator", action="store_true", help="also time the reference's eager torch loop on this GPU (c2/c3)")
@@ -307,12 +308,12 @@ def run_ours(args, rank, world, local_rank):
     # leaves clean lines -- a memset would leave 126 MB of dirty lines to be written back during the timed kernel), so no
     # launch can find the previous step's stores in the 126 MB L2 (the null denoiser leaves nothing between steps)
     cold = None
-    if world == 1 and args.config in ("c2", "c3") and not args.no_cold:
+    if world == 1 and not args.no_cold and (args.config in ("c2", "c3") or args.cold):
         flush = torch.zeros(128 << 20, dtype=torch.float32, device=dev)
         sampler._graph = None
         sampler.sample(den, noise=noise)
         evs = []
-        n_cold = 5
+        n_cold = 5 if K <= 30 else 1
         st_ptr = torch.cuda.current_stream(dev).cuda_stream
         for _ in range(n_cold):
             for k in range(K):

@@ -36,6 +36,16 @@
 #ifndef NI_STREAM_LOAD_POLICY
 #define NI_STREAM_LOAD_POLICY 0 /* flavour of the step kernel's loads when the launch footprint is >> L2 */
 #endif
+// launch_streams(): L2-friendly loads iff written <= NI_L2_KEEP_NUM/NI_L2_KEEP_DEN of the L2 and written >= traffic / NI_L2_KEEP_SHARE
+#ifndef NI_L2_KEEP_NUM
+#define NI_L2_KEEP_NUM 3
+#endif
+#ifndef NI_L2_KEEP_DEN
+#define NI_L2_KEEP_DEN 5
+#endif
+#ifndef NI_L2_KEEP_SHARE
+#define NI_L2_KEEP_SHARE 16
+#endif
 #ifndef NI_STORE_POLICY
 #define NI_STORE_POLICY 0 /* 0 plain st.global, 1 st.global.cs */
 #endif
@@ -804,7 +814,7 @@ bool launch_streams(const StepArgs &a, const NiStepDesc *d, int elem_size, int o
     int64_t read = (int64_t)(d->n_terms + (d->accumulate ? 1 : 0) + (a.x_in != nullptr ? 1 : 0)) * d->numel * elem_size;
     if (d->has_x0) read += (int64_t)(1 + (d->out1 != nullptr ? 1 : 0)) * d->numel * out_elem_size;
     const int64_t l2 = dev_info().l2_bytes;
-    return 5 * written > 3 * l2 || 16 * written < read + written;
+    return NI_L2_KEEP_DEN * written > NI_L2_KEEP_NUM * l2 || NI_L2_KEEP_SHARE * written < read + written;
 }
 
 template <typename T, typename TO, int VEC, bool STREAM>
