@@ -276,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     counted = ni.launch_count() - c0
     assert counted == launches_per_traj, (counted, launches_per_traj)
+    flavours = sampler.load_flavours()  # out0/out1 are patched into the descriptors by the trajectory above
     if args.no_graph:
         run = lambda: sampler.sample(den, noise=noise)
     else:
@@ -429,7 +430,8 @@ def run_ours(args, rank, world, local_rank):
                                f"null denoiser ({m} pre-generated N(0,1) model output(s) of {cout} channels re-read from HBM each step)",
                    "markov_fast_path": bool(sampler.plan.markov),
                    "shape": [batch] + list(shape), "eps0": args.eps0, "numa_bound_cpus": numa_cpus, "cuda_graph": not args.no_graph, "variant": args.variant, "opts": args.opt,
-                   "load_flavour": "auto per launch: ld.global.L1::no_allocate when the bytes it writes fit in 0.6 of the L2 and are >= 1/16 of its traffic, else plain ld.global (override: --opt load_policy=1|2)",
+                   "load_flavours_per_step": "".join(str(f) for f in flavours) if K <= 32 else f"{sum(flavours)} of {K} steps streaming",
+                   "load_flavour": "1 = plain ld.global, 0 = L1::no_allocate; auto per launch: ld.global.L1::no_allocate when the bytes it writes fit in 0.6 of the L2 and are >= 1/16 of its traffic, else plain ld.global (override: --opt load_policy=1|2)",
                    "l2": f"inputs larger than L2: per-trajectory working set {(sampler.state_bytes() + sum(o.numel() for o in outs) * esize) / 1e6:.0f} MB vs 126 MB L2",
                    "state_bytes": sampler.state_bytes()},
         "clocks": clk,

@@ -120,6 +120,10 @@ int ni_set_option(const char *name, int value);
 
 int ni_step(const NiStepDesc *desc_host, void *stream);
 
+/* Which load flavour ni_step would pick for this descriptor on the current device: 1 = streaming (plain ld.global),
+ * 0 = L2-friendly (ld.global.L1::no_allocate), negative = NI_ERR_*.  Launches nothing; reporting / tests only. */
+int ni_step_flavour(const NiStepDesc *desc_host);
+
 /* dst = scale * sum_t coeffs[t] * src[t].  The three reference `weighted_sum`s and
  * `euler_weighted_sum` (src/CIFAR10NaturalInference.py:233-238, src/ValidateNaturalInference.py:198-204,
  * src/SD3NaturalInference.py:157-168, :61-69) as one launch.  src_dtype F64 (the CIFAR loop keeps an

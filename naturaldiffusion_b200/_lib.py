@@ -84,6 +84,8 @@ def lib():
     L.ni_set_option.restype = C.c_int
     L.ni_step.argtypes = [C.POINTER(NiStepDesc), C.c_void_p]
     L.ni_step.restype = C.c_int
+    L.ni_step_flavour.argtypes = [C.POINTER(NiStepDesc)]
+    L.ni_step_flavour.restype = C.c_int
     L.ni_weighted_sum.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_int64,
                                   C.c_int, C.c_int, C.c_double, C.c_void_p]
     L.ni_weighted_sum.restype = C.c_int
@@ -98,8 +100,8 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_set_option", "ni_step", "ni_weighted_sum",
-                    "ni_philox_normal", "ni_to_pixel_u8")
+EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_set_option", "ni_step", "ni_step_flavour",
+                    "ni_weighted_sum", "ni_philox_normal", "ni_to_pixel_u8")
 
 
 def check(rc: int, what: str = "libni_b200"):

@@ -75,6 +75,9 @@ std::atomic<int> g_tma_ctas_per_sm{2};
 std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernel
 std::atomic<int> g_load_policy{0};   // step-kernel load flavour: 0 by launch footprint vs L2, 1 always L2-friendly (NA), 2 always streaming
 
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int dtype_size(int d) { return d == NI_F32 ? 4 : d == NI_F64 ? 8 : (d == NI_F16 || d == NI_BF16) ? 2 : 0; }
+
 int fail(int code, const char *fmt, ...)
 {
     va_list ap;
@@ -749,8 +752,6 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_pixel_kernel(const T *__restrict_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline int dtype_size(int d) { return d == NI_F32 ? 4 : d == NI_F64 ? 8 : (d == NI_F16 || d == NI_BF16) ? 2 : 0; }
 
 int check_launch(const char *what)
 {
@@ -802,17 +803,19 @@ const DevInfo &dev_info()
 // streamed history leaves first), which pays when they fit -- measured: up to ~0.6 of the L2, 67 MB written per launch
 // on the SD3 shapes (+2..11%) but not C2's 100 MB (-1.2%) -- and when they are a visible share of the traffic (DDPM-250
 // dense rows write 3 of ~250 tensors: streaming +1.7%).  Everything else streams.  profiles/r01_policy_sweep.txt.
-bool launch_streams(const StepArgs &a, const NiStepDesc *d, int elem_size, int out_elem_size)
+bool launch_streams(const NiStepDesc *d)
 {
     const int pol = g_load_policy.load(std::memory_order_relaxed);
     if (pol != 0) return pol == 2;
-    int64_t n_written = (a.x0_dst != nullptr ? 1 : 0) + (a.x_next != nullptr ? 1 : 0);
+    const int64_t esz = dtype_size(d->dtype), osz = dtype_size(d->has_x0 ? d->out_dtype : d->dtype);
+    const bool reads_x = d->has_x0 && d->x_in != nullptr && (d->a != 0.f || d->c_xin != 0.f);
+    int64_t n_written = (d->has_x0 && d->x0_dst != nullptr ? 1 : 0) + (d->x_next != nullptr ? 1 : 0);
     for (int g = 0; g < d->n_gen; ++g) n_written += d->gen_dst[g] != nullptr ? 1 : 0;
-    int64_t written = n_written * d->numel * elem_size;
-    if (a.x_next_lp != nullptr) written += d->numel * 2;
-    if (a.pixels != nullptr) written += d->numel;
-    int64_t read = (int64_t)(d->n_terms + (d->accumulate ? 1 : 0) + (a.x_in != nullptr ? 1 : 0)) * d->numel * elem_size;
-    if (d->has_x0) read += (int64_t)(1 + (d->out1 != nullptr ? 1 : 0)) * d->numel * out_elem_size;
+    int64_t written = n_written * d->numel * esz;
+    if (d->x_next_lp != nullptr) written += d->numel * 2;
+    if (d->pixels_u8 != nullptr) written += d->numel;
+    int64_t read = (int64_t)(d->n_terms + (d->accumulate ? 1 : 0) + (reads_x ? 1 : 0)) * d->numel * esz;
+    if (d->has_x0) read += (int64_t)(1 + (d->out1 != nullptr ? 1 : 0)) * d->numel * osz;
     const int64_t l2 = dev_info().l2_bytes;
     return NI_L2_KEEP_DEN * written > NI_L2_KEEP_NUM * l2 || NI_L2_KEEP_SHARE * written < read + written;
 }
@@ -838,7 +841,7 @@ template <typename T, typename TO, int VEC>
 int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
 {
     if constexpr (VEC > 1) { // the scalar (misaligned / ragged) path is not a bandwidth path: one flavour
-        if (launch_streams(a, d, (int)sizeof(T), (int)sizeof(TO))) return launch_step_pol<T, TO, VEC, true>(a, d, st);
+        if (launch_streams(d)) return launch_step_pol<T, TO, VEC, true>(a, d, st);
     }
     return launch_step_pol<T, TO, VEC, false>(a, d, st);
 }
@@ -938,6 +941,14 @@ int ni_set_option(const char *name, int value)
     if (!strcmp(name, "load_policy")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "load_policy must be 0..2"); g_load_policy = value; return NI_OK; }
     if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
     return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);
+}
+
+int ni_step_flavour(const NiStepDesc *d)
+{
+    if (d == nullptr) return fail(NI_ERR_INVALID, "ni_step_flavour: NULL descriptor");
+    if (d->numel < 0 || dtype_size(d->dtype) == 0 || (d->has_x0 && dtype_size(d->out_dtype) == 0)) return fail(NI_ERR_INVALID, "ni_step_flavour: bad sizes or dtypes");
+    if (d->n_terms < 0 || d->n_gen < 0 || d->n_gen > NI_MAX_GEN) return fail(NI_ERR_TOO_MANY, "ni_step_flavour: bad term counts");
+    return launch_streams(d) ? 1 : 0;
 }
 
 int ni_step(const NiStepDesc *d, void *stream)

@@ -140,6 +140,14 @@ class StepLaunch:
     def set_term_ptr(self, i: int, ptr: int):
         self._ptrs[i] = ptr
 
+    def flavour(self) -> int:
+        """1 = streaming loads, 0 = L2-friendly loads: what ni_step picks for this launch on the current device
+        (ni_step_flavour; launches nothing)."""
+        rc = _lib.lib().ni_step_flavour(C.byref(self.desc))
+        if rc < 0:
+            check(rc, "ni_step_flavour")
+        return rc
+
     def launch(self, stream: int):
         rc = _lib.lib().ni_step(C.byref(self.desc), stream)
         if rc != 0:

@@ -184,6 +184,12 @@ class NaturalInferenceSampler:
         self._launch_cache[key] = launches
         self._launches, self._launch_key = launches, key
 
+    def load_flavours(self) -> List[int]:
+        """Per step, the load flavour the prepared launches get (1 streaming / 0 L2-friendly; after a first sample())."""
+        if self._launches is None:
+            raise NiError("load_flavours() needs prepared launches: call sample() once")
+        return [row[0].flavour() for row in self._launches]
+
     def _check_out(self, o: torch.Tensor, k: int):
         if not o.is_cuda:
             raise NiError(f"denoiser output at step {k} must be a CUDA tensor")

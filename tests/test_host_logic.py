@@ -45,6 +45,38 @@ def test_struct_layout_matches_header(tmp_path):
     assert vals[1:] == [getattr(_lib.NiStepDesc, f).offset for f in fields]
 
 
+def test_load_flavour_rule_on_the_baseline_shapes():
+    """ni_step_flavour: the per-launch choice between streaming (1) and L2-friendly (0) loads.  Without a device the
+    library assumes a 126 MiB L2 (B200).  Expected values are the faster flavour measured on the B200
+    (profiles/r01_policy_sweep.txt); the DDPM first-order path is the one shape where the rule is 1.7% off."""
+    from naturaldiffusion_b200.ops import StepLaunch
+    F32, F16 = _lib.NI_F32, _lib.NI_F16
+
+    def flavour(numel, dt, m, n_terms, keep_x0=True, keep_gen=0):
+        L = StepLaunch(numel=numel, per_sample=numel // 64, dtype=dt, has_x0=True, x_in=0x1000, out0=0x2000, out1=0x3000 if m == 2 else 0,
+                       a=1.0, b0=1.0, b1=0.5, x0_dst=0x4000 if keep_x0 else 0, c_x0=1.0, terms=[(0x10000 + 16 * i, 0.1) for i in range(n_terms)],
+                       gens=[(i + 1, 0.1, 0x5000) for i in range(keep_gen)], x_next=0x6000)
+        return L.flavour()
+
+    c2, c3, c4, c5 = 4096 * 3072, 16384 * 3072, 1024 * 4096, 64 * 16 * 128 * 128
+    assert flavour(c2, F32, 1, 4) == 1 and flavour(c3, F32, 1, 4) == 1          # 100 / 400 MB written per launch: streams
+    assert flavour(c2, F32, 1, 1, keep_x0=False) == 0                            # C2 steps 0 and 9 write x_{k+1} only (50 MB)
+    assert flavour(c3, F32, 1, 1, keep_x0=False) == 1
+    assert flavour(c5, F16, 2, 1, keep_x0=False) == 0                            # SD3 first-order path: 33 MB written, +11% with NA loads
+    assert flavour(c5, F16, 2, 14) == 0 and flavour(c5, F16, 2, 5) == 0          # sharp / dense SD3 tables at B 64: 67 MB written
+    assert flavour(4 * c5, F16, 2, 10) == 1                                      # B 256: 268 MB written
+    assert flavour(c4, F32, 2, 200, keep_gen=1) == 1                             # dense DDPM-250 row: 3 of ~200 tensors written
+    assert flavour(c4, F32, 2, 0, keep_x0=False) == 0
+    try:
+        _lib.set_option("load_policy", 2)
+        assert flavour(c5, F16, 2, 1, keep_x0=False) == 1
+        _lib.set_option("load_policy", 1)
+        assert flavour(c3, F32, 1, 4) == 0
+    finally:
+        _lib.set_option("load_policy", 0)
+    assert ni.lib().ni_step_flavour(None) == -1
+
+
 def test_argument_validation_needs_no_gpu():
     L = ni.lib()
     assert L.ni_step(None, None) == -1 and b"NULL" in L.ni_last_error()
