@@ -417,9 +417,10 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cb = {"c2": batch, "c3": 4096, "c4": 32, "c5": 4, "c5s": 4}[args.config]
-        ts = time_cpu(args.config, cb, 2, 1)
+        reps = {"c2": 10, "c3": 3}.get(args.config, 2)  # about 10 s of CPU work
+        ts = time_cpu(args.config, cb, reps, 1)
         cpu = {"value": cb / min(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{cb}-sample batch of the same workload (full per-GPU batch is {batch}), best of 2 trajectories after 1 warm-up "
+               "sample": f"{cb}-sample batch of the same workload (full per-GPU batch is {batch}), best of {reps} trajectories after 1 warm-up "
                          f"({sum(ts):.1f} s CPU work); oracle port of the reference loop in the reference's dtypes; torch {torch.__version__} CPU, {cpu_model()}"}
 
     line = {
