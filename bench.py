@@ -224,6 +224,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from naturaldiffusion_b200.hostutil import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0)
     numa_cpus = None if args.no_numa else bind_to_gpu_numa_node(local_rank)  # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -416,6 +417,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core back, not only the GPU-local ones
         cb = {"c2": batch, "c3": 4096, "c4": 32, "c5": 4, "c5s": 4}[args.config]
         reps = {"c2": 10, "c3": 3}.get(args.config, 2)  # about 10 s of CPU work
         ts = time_cpu(args.config, cb, reps, 1)
