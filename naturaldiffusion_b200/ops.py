@@ -89,7 +89,7 @@ def to_pixel_u8(x: torch.Tensor, *, scale: float = 0.5, shift: float = 0.5, out:
 class StepLaunch:
     """One prepared ``ni_step`` launch: owns the ctypes descriptor and its host tables."""
 
-    __slots__ = ("desc", "_ptrs", "_coeffs", "_keep")
+    __slots__ = ("desc", "_ptrs", "_coeffs")
 
     def __init__(self, *, numel, per_sample, dtype, out_dtype=None, has_x0=True, x_in=0, out0=0, out1=0,
                  out_sample_stride=None, a=0.0, b0=0.0, b1=0.0, x0_dst=0, c_x0=0.0, c_xin=0.0,
@@ -135,10 +135,6 @@ class StepLaunch:
         d.pixels_u8 = pixels_u8 or None
         d.px_scale, d.px_shift, d.px_channels = float(px_scale), float(px_shift), int(px_channels)
         self.desc = d
-        self._keep = None
-
-    def set_term_ptr(self, i: int, ptr: int):
-        self._ptrs[i] = ptr
 
     def flavour(self) -> int:
         """1 = streaming loads, 0 = L2-friendly loads: what ni_step picks for this launch on the current device
