@@ -59,6 +59,19 @@ class CoeffTriple:
         """Same array names and order as src/Utils.py:49."""
         np.savez(path, past_xstart_coeff=self.A, past_epsilon_coeff=self.B, node_coeff=self.node)
 
+    def save_companion_csv(self, path):
+        """The human-readable table `save_coeff_matrix` writes next to each npz (src/Utils.py:36-45): A rounded to 3
+        decimals, columns = the K node times that produced each x0, index = the K times reached, plus a `sum` column.
+        Times print as %03d on the discrete grid (mean t > 1) and %0.3f on the continuous one.  Written without pandas;
+        byte-identical to the files under the reference's results/ (tests/test_host_logic.py)."""
+        t = self.node[:, 0]
+        names = [("%03d" % v) if t.mean() > 1 else ("%0.3f" % v) for v in t]
+        cell = lambda v: repr(float(v))  # pandas' default float formatting is the shortest round-trip repr
+        with open(path, "w", newline="") as f:
+            f.write("," + ",".join(names[:-1]) + ",sum\n")
+            for k in range(self.K):
+                f.write(names[k + 1] + "," + ",".join(cell(v) for v in self.A[k].round(3)) + "," + cell(self.A[k].sum().round(3)) + "\n")
+
     @classmethod
     def from_sd3_table(cls, W, sigmas, name="") -> "CoeffTriple":
         """csv weight table + scheduler sigmas (length K+1, last = 0) -> common form:

@@ -219,6 +219,24 @@ def test_npz_roundtrip_and_shapes(tmp_path, weights_dir):
     assert np.array_equal(flow_match_sigmas(28), O.sd3_sigmas(28))
 
 
+def test_companion_csv_writer_reproduces_the_reference_files(golden_dir, tmp_path):
+    """`save_coeff_matrix` (src/Utils.py:30-45) writes a rounded csv next to every npz; CoeffTriple.save_companion_csv
+    reproduces the shipped files byte for byte (up to the CRLF of the Windows box they were written on) -- discrete
+    (%03d) and continuous (%0.3f) time labels, -0.0 entries, the sum column.  All 44 files when the reference tree is here."""
+    import glob
+    m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
+    cases = [(os.path.join(golden_dir, "reference_csv", os.path.basename(k) + ".csv"), m[k + "/A"], m[k + "/B"], m[k + "/node"])
+             for k in ("ddim/ddim_018", "ddpm/ddpm_sympy_018", "dpmsolverpp/dpmsolverpp2s_018", "deis/deis_tab_100")]
+    for npz in sorted(glob.glob("/root/reference/results/*/*.npz")):
+        if os.path.isfile(npz[:-4] + ".csv"):
+            cases.append((npz[:-4] + ".csv",) + tuple(np.load(npz).values()))
+    assert len(cases) >= 4
+    for csv_path, A, B, node in cases:
+        out = tmp_path / "t.csv"
+        CoeffTriple(A, B, node).save_companion_csv(out)
+        assert out.read_bytes() == open(csv_path, "rb").read().replace(b"\r\n", b"\n"), csv_path
+
+
 def test_generators_match_reference_matrices(golden_dir):
     m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
     for fam, fn in (("ddim", generators.ddim_triple), ("ddpm", generators.ddpm_triple)):
