@@ -105,6 +105,29 @@ def load_weight_csv(path) -> np.ndarray:
     return np.array([[float(v) for v in r[1:]] for r in rows[1:]], dtype=np.float64)
 
 
+def save_weight_csv(W, sigmas, path):
+    """Write an SD3 weight table in the layout of weights/sd3_step_28_weight*.csv (what `pd.read_csv(path, index_col=0)`
+    at src/SD3NaturalInference.py:196 expects): header and index are sigma_1..sigma_K as %.2f, cells the shortest
+    round-trip float repr.  `sigmas` has K+1 entries (sigma_0 = 1 first)."""
+    W = np.asarray(W, dtype=np.float64)
+    names = ["%.2f" % float(v) for v in list(sigmas)[1:]]
+    if W.shape != (len(names), len(names)):
+        raise ValueError(f"W is {W.shape}, expected ({len(names)}, {len(names)}) for {len(names) + 1} sigmas")
+    with open(path, "w", newline="") as f:
+        f.write("," + ",".join(names) + "\n")
+        for k, row in enumerate(W):
+            f.write(names[k] + "," + ",".join(repr(float(v)) for v in row) + "\n")
+
+
+def flow_euler_weight_table(sigmas) -> np.ndarray:
+    """The table of plain flow-matching Euler in the csv's own units: W[k,j] = round(100 (sigma_j - sigma_{j+1}), 2) for
+    j <= k.  With the FlowMatchEuler grid this IS weights/sd3_step_28_weight.csv (every cell); `euler_weighted_sum`
+    (src/SD3NaturalInference.py:61-69) carries the same differences unrounded."""
+    sig = np.asarray(sigmas, dtype=np.float64)
+    d = np.round(100.0 * (sig[:-1] - sig[1:]), 2)
+    return np.tril(np.tile(d, (len(d), 1)))
+
+
 def flow_match_sigmas(num_step=28, shift=3.0, num_train=1000) -> np.ndarray:
     """Sigma grid of diffusers' FlowMatchEulerDiscreteScheduler.set_timesteps (what
     src/SD3NaturalInference.py:188-190 reads from the pipeline), float32, trailing 0."""

@@ -237,6 +237,27 @@ def test_companion_csv_writer_reproduces_the_reference_files(golden_dir, tmp_pat
         assert out.read_bytes() == open(csv_path, "rb").read().replace(b"\r\n", b"\n"), csv_path
 
 
+def test_sd3_weight_table_writer(weights_dir, tmp_path):
+    """save_weight_csv writes what src/SD3NaturalInference.py:196 reads: the generated default table reproduces the
+    shipped csv byte for byte (up to CRLF); the hand-edited sharp table (integer cells) round-trips by value."""
+    from naturaldiffusion_b200.coeffs import save_weight_csv
+    sig = flow_match_sigmas(28)
+    for name, exact in (("sd3_step_28_weight.csv", True), ("sd3_step_28_weight_sharp.csv", False)):
+        src = os.path.join(weights_dir, name)
+        W = load_weight_csv(src)
+        out = tmp_path / name
+        save_weight_csv(W, sig, out)
+        assert np.array_equal(load_weight_csv(out), W)
+        if exact:
+            assert out.read_bytes() == open(src, "rb").read().replace(b"\r\n", b"\n")
+    # the default table IS round(100 * (sigma_i - sigma_{i+1}), 2) on every row (SURVEY 8a a8)
+    W = load_weight_csv(os.path.join(weights_dir, "sd3_step_28_weight.csv"))
+    from naturaldiffusion_b200.coeffs import flow_euler_weight_table
+    assert np.array_equal(W, flow_euler_weight_table(sig))
+    with pytest.raises(ValueError):
+        save_weight_csv(W[:5], sig, tmp_path / "bad.csv")
+
+
 def test_generators_match_reference_matrices(golden_dir):
     m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
     for fam, fn in (("ddim", generators.ddim_triple), ("ddpm", generators.ddpm_triple)):
