@@ -330,3 +330,45 @@ def dpm_solver_3s_triple(steps: int, plus_plus: bool = False, t_T=1.0, t_0=1e-3)
             x = (np.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - ns.sigma(t) * np.expm1(h) * e_s
                  - (1.0 / r2) * ns.sigma(t) * (np.expm1(h) / h - 1.0) * (e_s2 - e_s))
     return tr.finish(x, ts[-1], name=("dpmsolverpp3s" if plus_plus else "dpmsolver3s") + f"_{3 * steps:03d}")
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's optimised matrices (weights/step_{5,10,15}_weight_*.npz): relative patterns
+# ----------------------------------------------------------------------------------------------
+def vp_quadratic_node(K: int, t_T=1.0, t_0=1e-3, schedule: "VPLinearSchedule" = None) -> np.ndarray:
+    """node_coeff (K+1, 3) = (t, alpha, sigma) on the quadratic time grid with VP-linear marginals: what the shipped
+    weights/step_*.npz carry (theirs to float32 round-off: t to 1e-7, sigma to 5e-8; alpha exactly)."""
+    ns = schedule or VPLinearSchedule()
+    t = quadratic_time_grid(K, t_T, t_0)
+    return np.stack([t, [ns.alpha(v) for v in t], [ns.sigma(v) for v in t]], axis=1)
+
+
+def relative_patterns(triple: CoeffTriple, decimals=2):
+    """Each row of A relative to its diagonal, rounded: the form the optimised matrices were authored in (e.g. row 5 of
+    step_15_weight_173 is [0.30, -0.14, 0.56, -0.77, 1] over its band).  Returns K arrays of length k+1."""
+    out = []
+    for k in range(triple.K):
+        r = triple.A[k, : k + 1] / triple.A[k, k]
+        out.append(r if decimals is None else np.round(r, decimals))
+    return out
+
+
+def relative_pattern_triple(patterns, node, name="") -> CoeffTriple:
+    """Deterministic Natural Inference matrix from per-row relative patterns: row k = alpha_{k+1} * pattern_k / sum(pattern_k)
+    (so that rowsum(A) = alpha, the signal coefficient of the marginal) and B[k,0] = sigma_{k+1} on the initial noise --
+    the invariants of weights/step_*.npz.  pattern_k may be shorter than k+1: it is right-aligned
+    on the diagonal (a band)."""
+    node = np.asarray(node, dtype=np.float64)
+    K = len(patterns)
+    if node.shape != (K + 1, 3):
+        raise ValueError(f"node must be ({K + 1}, 3) for {K} pattern rows")
+    A, B = np.zeros((K, K)), np.zeros((K, K + 1))
+    for k, pat in enumerate(patterns):
+        pat = np.asarray(pat, dtype=np.float64)
+        if pat.ndim != 1 or not 1 <= len(pat) <= k + 1:
+            raise ValueError(f"pattern {k} must have between 1 and {k + 1} entries")
+        if pat.sum() == 0:
+            raise ValueError(f"pattern {k} sums to zero")
+        A[k, k + 1 - len(pat): k + 1] = node[k + 1, 1] * pat / pat.sum()
+        B[k, 0] = node[k + 1, 2]
+    return CoeffTriple(A, B, node, name=name)

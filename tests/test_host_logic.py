@@ -258,6 +258,25 @@ def test_sd3_weight_table_writer(weights_dir, tmp_path):
         save_weight_csv(W[:5], sig, tmp_path / "bad.csv")
 
 
+def test_optimised_matrices_rebuild_from_relative_patterns(weights_dir):
+    """weights/step_{10,15}_weight_*.npz are 2-decimal relative patterns scaled to rowsum = alpha, B[:,0] = sigma:
+    extracting the patterns and rebuilding gives the shipped A to 1 ulp; step_5 needs its unrounded ratios.  The
+    quadratic VP node grid matches the stored one to float32 round-off."""
+    for name, dec in (("step_10_weight_42", 2), ("step_15_weight_173", 2), ("step_5_weight_00", None)):
+        t = CoeffTriple.from_npz(os.path.join(weights_dir, name + ".npz"))
+        pats = generators.relative_patterns(t, decimals=dec)
+        r = generators.relative_pattern_triple(pats, t.node)
+        assert np.abs(r.A - t.A).max() < 5e-16 and np.array_equal(r.B, t.B)
+        band = [p[np.flatnonzero(p)[0]:] for p in pats]          # right-aligned band form
+        assert np.abs(generators.relative_pattern_triple(band, t.node).A - r.A).max() < 5e-16
+        node = generators.vp_quadratic_node(t.K)
+        assert np.abs(node[:, 0] - t.node[:, 0]).max() < 2e-7 and np.abs(node[:, 1:] - t.node[:, 1:]).max() < 2e-6
+        assert build_plan(r).n_x0_slots == build_plan(t).n_x0_slots
+    assert list(generators.relative_patterns(CoeffTriple.from_npz(os.path.join(weights_dir, "step_15_weight_173.npz")))[5]) == [0, 0.30, -0.14, 0.56, -0.77, 1]
+    with pytest.raises(ValueError):
+        generators.relative_pattern_triple([[1.0], [1.0, -1.0]], generators.vp_quadratic_node(2))
+
+
 def test_generators_match_reference_matrices(golden_dir):
     m = np.load(os.path.join(golden_dir, "reference_matrices.npz"))
     for fam, fn in (("ddim", generators.ddim_triple), ("ddpm", generators.ddpm_triple)):
