@@ -44,7 +44,7 @@ def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, 
     dev = torch.device("cuda", lr)
     if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl", device_id=dev)
-    triple = ni.CoeffTriple.from_npz(os.path.join(ROOT, "tests", "golden", "reference_weights", weights))
+    triple = ni.CoeffTriple.from_npz(os.path.join(ROOT, "naturaldiffusion_b200", "data", "weights", weights))
     torch.manual_seed(0)
     model = (NCSNppVP(nf=32, num_res_blocks=1) if small_model else NCSNppVP()).reinit_output().to(dev).eval()
     den = ncsnpp_denoiser(model, triple.node)

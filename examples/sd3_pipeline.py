@@ -24,7 +24,7 @@ import torch  # noqa: E402
 from naturaldiffusion_b200 import presets  # noqa: E402
 from naturaldiffusion_b200.denoisers import MMDiT, mmdit_sd3_medium  # noqa: E402
 
-WEIGHTS = os.path.join(ROOT, "tests", "golden", "reference_weights")
+WEIGHTS = os.path.join(ROOT, "naturaldiffusion_b200", "data", "weights")
 
 
 @torch.no_grad()

@@ -24,7 +24,8 @@
  *                                   key = (seed.lo, seed.hi))
  *     u(r) = fma((float)r, 2^-32, 2^-33);  v(r) = fma((float)r, 2^-31, 2^-32)
  *     rad = sqrt(-2 ln u(r0)); z0 = rad*cospi(v(r1)); z1 = rad*sinpi(v(r1)); (r2,r3) -> z2,z3
- *     (device: precise logf, SFU sqrt/sin/cos -- within 6e-6 of the fp64 evaluation of these formulas, 3e-7 typical)
+ *     (device: -2 ln u through MUFU.LG2 with a 4-term series for u > 31/32, SFU sqrt/sin/cos -- within 6e-6 of the
+ *     fp64 evaluation of these formulas, 3e-7 typical; ni_debug_box_muller exposes the transform for edge-case tests)
  *   Keyed by the GLOBAL element index, so a batch sharded over G GPUs (each shard passing
  *   its own elem_offset) draws exactly the tensor a single GPU would.
  */
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NI_ABI_VERSION 3
+#define NI_ABI_VERSION 4
 #define NI_MAX_TERMS 512 /* stored history/noise terms per launch; longer rows: call twice with accumulate */
 #define NI_MAX_GEN 4     /* noise terms generated in-kernel per launch */
 
@@ -91,6 +92,9 @@ typedef struct NiStepDesc {
     void *gen_dst[NI_MAX_GEN]; /* where to keep the generated tensor for later rows, or NULL */
     uint64_t philox_seed;
     uint64_t elem_offset;      /* global index of this shard's element 0 */
+    const uint64_t *elem_offset_dev; /* optional DEVICE counter added to elem_offset when the kernel runs: a captured CUDA graph
+                                  draws new noise on every replay (advance it with ni_counter_add inside the graph), which is how
+                                  successive batches get fresh randn like src/ValidateNaturalInference.py:345,359 per call */
 
     int32_t accumulate;        /* 1: x_next += (this launch) -- used to chain rows longer than NI_MAX_TERMS */
     float bias;                /* constant added to x_next (output stage of latent models: x/scaling_factor + shift_factor,
@@ -109,8 +113,11 @@ int ni_version(void);
 const char *ni_last_error(void);
 /* kernels launched by this library in this process so far (bench.py's `gpu_launches`) */
 int64_t ni_launch_count(void);
+/* how many of those were ni_step launches served by the row-shape-specialised kernels (ni_step_lean.cu) */
+int64_t ni_lean_launch_count(void);
 
-/* Tuning knobs, process-wide: "variant" 0 auto | 1 direct-load kernel | 2 TMA-staged kernel when eligible;
+/* Tuning knobs, process-wide: "variant" 0 auto (row-shape-specialised kernels, generic kernel for what they do not cover)
+ * | 1 generic direct-load kernel | 2 TMA-staged kernel when eligible;
  * "tma_max_stages" 2..32; "tma_warps" 1..16; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4; "pdl" 0|1 (programmatic
  * dependent launch of the direct-load step kernel, default 1); "load_policy" 0 auto | 1 L2-friendly loads
  * (ld.global.L1::no_allocate) | 2 streaming loads (plain ld.global) -- auto picks L2-friendly loads when what the
@@ -136,6 +143,18 @@ int ni_weighted_sum(const void *const *src_ptrs_host, const double *coeffs_host,
  * src/SD3NaturalInference.py:182 and lets tests feed the reference the very tensors the fused step draws. */
 int ni_philox_normal(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id,
                      uint64_t elem_offset, void *stream);
+
+/* Same, with a DEVICE counter added to elem_offset at run time (see NiStepDesc.elem_offset_dev). */
+int ni_philox_normal_at(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id,
+                        uint64_t elem_offset, const uint64_t *elem_offset_dev, void *stream);
+
+/* *counter_dev += delta on `stream` (one tiny launch; graph-capturable).  The loop-level sampler ends each captured
+ * trajectory with it so that replay i draws the noise of samples [first + i*B, first + (i+1)*B). */
+int ni_counter_add(uint64_t *counter_dev, uint64_t delta, void *stream);
+
+/* Test hook: the Box-Muller transform of the noise contract on caller-chosen Philox words, (za, zb)[i] from
+ * (ra, rb)[i] -- lets tests hit u -> 1, the series/LG2 switch-over and the 6.7-sigma tail directly. */
+int ni_debug_box_muller(const uint32_t *ra, const uint32_t *rb, float *za, float *zb, int64_t n, void *stream);
 
 /* Output stage (src/CIFAR10NaturalInference.py:308-309 with :212-216): NCHW float -> NHWC uint8,
  * u8 = trunc(clip((x*scale + shift)*255, 0, 255)); scale = shift = 0.5 is the inverse scaler of

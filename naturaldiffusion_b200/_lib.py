@@ -13,7 +13,7 @@ import os
 NI_F32, NI_F16, NI_BF16, NI_F64 = 0, 1, 2, 3
 NI_MAX_TERMS = 512
 NI_MAX_GEN = 4
-NI_ABI_VERSION = 3
+NI_ABI_VERSION = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NI_B200_LIB", os.path.join(_HERE, "libni_b200.so"))
@@ -50,6 +50,7 @@ class NiStepDesc(C.Structure):
         ("gen_dst", C.c_void_p * NI_MAX_GEN),
         ("philox_seed", C.c_uint64),
         ("elem_offset", C.c_uint64),
+        ("elem_offset_dev", C.c_void_p),
         ("accumulate", C.c_int32),
         ("bias", C.c_float),
         ("x_next", C.c_void_p),
@@ -80,6 +81,7 @@ def lib():
     L.ni_version.restype = C.c_int
     L.ni_last_error.restype = C.c_char_p
     L.ni_launch_count.restype = C.c_int64
+    L.ni_lean_launch_count.restype = C.c_int64
     L.ni_set_option.argtypes = [C.c_char_p, C.c_int]
     L.ni_set_option.restype = C.c_int
     L.ni_step.argtypes = [C.POINTER(NiStepDesc), C.c_void_p]
@@ -91,6 +93,12 @@ def lib():
     L.ni_weighted_sum.restype = C.c_int
     L.ni_philox_normal.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     L.ni_philox_normal.restype = C.c_int
+    L.ni_philox_normal_at.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.ni_philox_normal_at.restype = C.c_int
+    L.ni_counter_add.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ni_counter_add.restype = C.c_int
+    L.ni_debug_box_muller.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.ni_debug_box_muller.restype = C.c_int
     L.ni_to_pixel_u8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_float, C.c_void_p]
     L.ni_to_pixel_u8.restype = C.c_int
@@ -100,8 +108,9 @@ def lib():
     return L
 
 
-EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_set_option", "ni_step", "ni_step_flavour",
-                    "ni_weighted_sum", "ni_philox_normal", "ni_to_pixel_u8")
+EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_lean_launch_count", "ni_set_option", "ni_step", "ni_step_flavour",
+                    "ni_weighted_sum", "ni_philox_normal", "ni_philox_normal_at", "ni_counter_add", "ni_debug_box_muller",
+                    "ni_to_pixel_u8")
 
 
 def check(rc: int, what: str = "libni_b200"):
@@ -116,3 +125,7 @@ def set_option(name: str, value: int):
 
 def launch_count() -> int:
     return int(lib().ni_launch_count())
+
+
+def lean_launch_count() -> int:
+    return int(lib().ni_lean_launch_count())

@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "csrc", "ni_kernels.cu")
+CSRC = os.path.join(HERE, "csrc")
+SRCS = [os.path.join(CSRC, n) for n in ("ni_kernels.cu", "ni_step_lean.cu")]
+SRC = SRCS[0]
 HDR = os.path.join(ROOT, "include", "ni_b200.h")
+DEPS = SRCS + [HDR, os.path.join(CSRC, "ni_common.cuh")]
 OUT = os.path.join(HERE, "libni_b200.so")
 
 NVCC_FLAGS = [
@@ -33,13 +36,13 @@ def needs_build(out=OUT) -> bool:
     if not os.path.isfile(out):
         return True
     t = os.path.getmtime(out)
-    return any(os.path.getmtime(p) > t for p in (SRC, HDR, __file__))
+    return any(os.path.getmtime(p) > t for p in DEPS + [__file__])
 
 
 def build(force: bool = False, defines=(), out: str = OUT, verbose: bool = False) -> str:
     if not force and not defines and not needs_build(out):
         return out
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), *defines, "-o", out, SRC]
+    cmd = [find_nvcc(), *NVCC_FLAGS, "--threads", "0", "-I", os.path.join(ROOT, "include"), *defines, "-o", out, *SRCS]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -34,8 +34,16 @@ class CoeffTriple:
         K = self.A.shape[0]
         if self.A.shape != (K, K):
             raise ValueError(f"past_xstart_coeff must be square, got {self.A.shape}")
-        if self.B.shape == (K, K):  # weights/*.npz flavour: only column 0 is used by the CIFAR loop
-            self.B = np.concatenate([self.B, np.zeros((K, 1))], axis=1)
+        if self.B.shape == (K, K):
+            # weights/*.npz flavour.  Its reader (src/CIFAR10NaturalInference.py:303) uses column 0 only -- B[kk,0]*noise
+            # with the single initial tensor -- so any other column is ignored here too (with a warning) instead of being
+            # promoted to per-step fresh noise, which would silently run a different, stochastic sampler.
+            if np.any(self.B[:, 1:] != 0):
+                import warnings
+                warnings.warn("K x K past_epsilon_coeff has non-zero columns >= 1; like the reference's CIFAR loop only column 0 "
+                              "(the initial noise) is used", stacklevel=3)
+            col0 = self.B[:, :1]
+            self.B = np.concatenate([col0, np.zeros((K, K))], axis=1)
         if self.B.shape != (K, K + 1):
             raise ValueError(f"past_epsilon_coeff must be (K,K) or (K,K+1), got {self.B.shape}")
         if self.node.shape != (K + 1, 3):

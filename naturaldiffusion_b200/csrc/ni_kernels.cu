@@ -11,31 +11,11 @@
 //   * tables (pointers, coefficients) in kernel parameters: no allocation, no sync,
 //     CUDA-graph capturable.
 // Reference semantics: see include/ni_b200.h (each entry point cites file:line).
-#include "ni_b200.h"
+#include "ni_common.cuh"
 
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <cuda_runtime.h>
-
-#include <atomic>
 #include <cstdarg>
 #include <cstdio>
-#include <cstring>
-#include <type_traits>
 
-// 128-bit load flavours (SASS): 0 plain ld.global (LDG.E.128), 1 ld.global.L1::no_allocate (LDG.E.NA.128), 2 ld.global.cs
-// (evict-first), 4 plain + L2::256B prefetch.  Measured on B200 (profiles/r01_policy_sweep.txt): when a launch streams far
-// more than the 126 MB L2 can hold (C2, C3) plain loads are 1.2% / 3.8% faster than NA loads -- NA-loaded lines are the
-// first to leave L2, so the dirty lines of the stores pile up and drain in bursts; evict-first STORES with NA loads recover
-// the same 3.4% on C3 -- while on launches whose tensors fit in L2 (SD3 first-order path, 33 MB tensors) NA loads are 11%
-// faster because the x_{k+1} just written survives until the next step reads it.  The step kernel is therefore built in
-// both flavours and the host picks per launch (see launch_streams); everything else uses NI_LOAD_POLICY.
-#ifndef NI_LOAD_POLICY
-#define NI_LOAD_POLICY 1
-#endif
-#ifndef NI_STREAM_LOAD_POLICY
-#define NI_STREAM_LOAD_POLICY 0 /* flavour of the step kernel's loads when the launch footprint is >> L2 */
-#endif
 // launch_streams(): L2-friendly loads iff written <= NI_L2_KEEP_NUM/NI_L2_KEEP_DEN of the L2 and written >= traffic / NI_L2_KEEP_SHARE
 #ifndef NI_L2_KEEP_NUM
 #define NI_L2_KEEP_NUM 3
@@ -46,37 +26,22 @@
 #ifndef NI_L2_KEEP_SHARE
 #define NI_L2_KEEP_SHARE 16
 #endif
-#ifndef NI_STORE_POLICY
-#define NI_STORE_POLICY 0 /* 0 plain st.global, 1 st.global.cs */
-#endif
-// Geometry of the direct-load kernels, chosen by the sweep in profiles/r01_sweep.txt: 128-thread CTAs, registers
-// capped at 48 (10 CTAs = 40 warps per SM) and up to 8 independent 128-bit loads per thread.  Full occupancy
-// (<= 32 registers) and 72-register / 24-warp builds were both ~8% slower.
-#ifndef NI_BLOCK
-#define NI_BLOCK 128
-#endif
-#ifndef NI_TERM_BATCH_MAX
-#define NI_TERM_BATCH_MAX 8 /* independent 128-bit term loads issued back to back per thread */
-#endif
-#ifndef NI_MIN_BLOCKS
-#define NI_MIN_BLOCKS 10 /* __launch_bounds__ second argument for the direct-load step kernel */
-#endif
+
+namespace ni {
 
 namespace {
-
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_lean_launches{0};
 // tuning knobs (ni_set_option): which step kernel, and the TMA kernel's geometry
-std::atomic<int> g_variant{0};       // 0 auto, 1 always the LDG kernel, 2 the TMA kernel whenever eligible
+std::atomic<int> g_variant{0};       // 0 auto (lean kernels, generic fallback), 1 always the generic direct-load kernel, 2 the TMA kernel whenever eligible
 std::atomic<int> g_tma_max_stages{32};
 std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
 std::atomic<int> g_tma_ctas_per_sm{2};
-std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernel
+std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernels
 std::atomic<int> g_load_policy{0};   // step-kernel load flavour: 0 by launch footprint vs L2, 1 always L2-friendly (NA), 2 always streaming
-
-inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline int dtype_size(int d) { return d == NI_F32 ? 4 : d == NI_F64 ? 8 : (d == NI_F16 || d == NI_BF16) ? 2 : 0; }
+} // namespace
 
 int fail(int code, const char *fmt, ...)
 {
@@ -87,227 +52,38 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-// ------------------------------------------------------------------------------------------
-// raw vector loads / stores with cache policy
-// ------------------------------------------------------------------------------------------
-template <int POL> __device__ __forceinline__ uint4 ld128_pol(const void *p)
+int check_launch(const char *what)
 {
-    uint4 r;
-    if constexpr (POL == 1) asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else if constexpr (POL == 2) asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else if constexpr (POL == 4) asm volatile("ld.global.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint2 ld64(const void *p)
-{
-    uint2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st128(void *p, uint4 v)
-{
-#if NI_STORE_POLICY == 1
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#else
-    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-#endif
-}
-__device__ __forceinline__ void st64(void *p, uint2 v)
-{
-    asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(NI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return NI_OK;
 }
 
-template <typename T> __device__ __forceinline__ float to_f(T v);
-template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
-template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <typename T> __device__ __forceinline__ T from_f(float f);
-template <> __device__ __forceinline__ float from_f<float>(float f) { return f; }
-template <> __device__ __forceinline__ __half from_f<__half>(float f) { return __float2half_rn(f); }
-template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float f) { return __float2bfloat16_rn(f); }
+int opt_pdl() { return g_pdl.load(std::memory_order_relaxed); }
+void count_lean_launch() { g_lean_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// VEC elements of T <-> registers.  VEC*sizeof(T) is 2, 4 (scalar path), 8, 16 or 32 bytes.
-template <typename T, int VEC> struct Raw {
-    static constexpr int BYTES = VEC * (int)sizeof(T);
-    static constexpr int WORDS = BYTES >= 4 ? BYTES / 4 : 1;
-    uint32_t w[WORDS];
-};
-
-template <typename T, int VEC, int POL = NI_LOAD_POLICY> __device__ __forceinline__ Raw<T, VEC> load_raw(const T *p)
+const DevInfo &dev_info()
 {
-    Raw<T, VEC> r;
-    constexpr int BYTES = Raw<T, VEC>::BYTES;
-    if constexpr (BYTES == 32) {
-        uint4 a = ld128_pol<POL>(p), b = ld128_pol<POL>(reinterpret_cast<const char *>(p) + 16);
-        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
-    } else if constexpr (BYTES == 16) {
-        uint4 a = ld128_pol<POL>(p);
-        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
-    } else if constexpr (BYTES == 8) {
-        uint2 a = ld64(p);
-        r.w[0] = a.x; r.w[1] = a.y;
-    } else if constexpr (BYTES == 4) {
-        r.w[0] = *reinterpret_cast<const uint32_t *>(p);
-    } else {
-        r.w[0] = *reinterpret_cast<const uint16_t *>(p);
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo info = {148, 126 << 20};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev) {
+        int sms = 0, l2 = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+        info.sms = sms > 0 ? sms : 148;
+        info.l2_bytes = l2 > 0 ? l2 : (126 << 20);
+        cached_dev = dev;
     }
-    return r;
+    return info;
 }
 
-template <typename T, int VEC> __device__ __forceinline__ void unpack(const Raw<T, VEC> &r, float (&f)[VEC])
-{
-    if constexpr (sizeof(T) == 4) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) f[i] = __uint_as_float(r.w[i]);
-    } else if constexpr (VEC == 1) {
-        unsigned short s = (unsigned short)r.w[0];
-        T t;
-        memcpy(&t, &s, 2);
-        f[0] = to_f<T>(t);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC / 2; ++i) {
-            if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
-                __half2 h;
-                memcpy(&h, &r.w[i], 4);
-                float2 v = __half22float2(h);
-                f[2 * i] = v.x; f[2 * i + 1] = v.y;
-            } else {
-                // bf16 -> f32 is a 16-bit shift
-                f[2 * i] = __uint_as_float(r.w[i] << 16);
-                f[2 * i + 1] = __uint_as_float(r.w[i] & 0xffff0000u);
-            }
-        }
-    }
-}
-
-template <typename T, int VEC> __device__ __forceinline__ Raw<T, VEC> pack(const float (&f)[VEC])
-{
-    Raw<T, VEC> r;
-    if constexpr (sizeof(T) == 4) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) r.w[i] = __float_as_uint(f[i]);
-    } else if constexpr (VEC == 1) {
-        T t = from_f<T>(f[0]);
-        unsigned short s;
-        memcpy(&s, &t, 2);
-        r.w[0] = s;
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC / 2; ++i) {
-            if constexpr (std::is_same<T, __half>::value) {
-                __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                memcpy(&r.w[i], &h, 4);
-            } else {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                memcpy(&r.w[i], &h, 4);
-            }
-        }
-    }
-    return r;
-}
-
-template <typename T, int VEC> __device__ __forceinline__ void store_raw(T *p, const Raw<T, VEC> &r)
-{
-    constexpr int BYTES = Raw<T, VEC>::BYTES;
-    if constexpr (BYTES == 32) {
-        st128(p, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
-        st128(reinterpret_cast<char *>(p) + 16, make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]));
-    } else if constexpr (BYTES == 16) {
-        st128(p, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
-    } else if constexpr (BYTES == 8) {
-        st64(p, make_uint2(r.w[0], r.w[1]));
-    } else if constexpr (BYTES == 4) {
-        *reinterpret_cast<uint32_t *>(p) = r.w[0];
-    } else {
-        *reinterpret_cast<uint16_t *>(p) = (uint16_t)r.w[0];
-    }
-}
-
-// round-trip through the storage type (what a later step will read back)
-template <typename T> __device__ __forceinline__ float round_to(float f)
-{
-    if constexpr (sizeof(T) == 4) return f;
-    else return to_f<T>(from_f<T>(f));
-}
-
-// ------------------------------------------------------------------------------------------
-// Philox4x32-10 + Box-Muller (noise contract in include/ni_b200.h; CPU twin: oracle/philox_oracle.c)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return c;
-}
-
-// Box-Muller on two Philox words.  The logarithm stays the precise logf: it alone decides the accuracy of small radii
-// (u near 1).  The radius square root and the angle use the SFU: sqrt.approx (rel. 2^-23) and sin/cos.approx on an
-// argument reduced to (-pi, pi] (abs. 2^-20.9) -- worst case |z - exact| < 4e-6 at the 6.7-sigma tail, ~3e-7 typical --
-// which cuts the generator from ~270 to ~190 SASS instructions per 4 normals.  Steps that draw fresh noise for every
-// element (DDPM ancestral, first-order path: 4 tensor transfers per step) are issue-bound by exactly this code.
-// NI_PRECISE_NORMAL restores sqrtf / sincospif.
-__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float &za, float &zb)
-{
-    const float u = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float v = fmaf(__uint2float_rn(rb), 4.6566128730773926e-10f, 2.3283064365386963e-10f);
-#ifdef NI_PRECISE_NORMAL
-    const float rad = sqrtf(-2.0f * logf(u));
-    float s, c;
-    sincospif(v, &s, &c);
-    za = rad * c;
-    zb = rad * s;
-#else
-    float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * logf(u)));
-    // cospi(v) = -cos(pi (v - 1)), sinpi(v) = -sin(pi (v - 1)); v in (0, 2] -> argument in (-pi, pi]
-    const float ang = 3.14159265358979323846f * (v - 1.0f);
-    za = -rad * __cosf(ang);
-    zb = -rad * __sinf(ang);
-#endif
-}
-
-__device__ __forceinline__ void normal4(uint64_t group, uint64_t tensor_id, uint32_t k0, uint32_t k1, float (&z)[4])
-{
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), (uint32_t)tensor_id, (uint32_t)(tensor_id >> 32)), k0, k1);
-    box_muller(r.x, r.y, z[0], z[1]);
-    box_muller(r.z, r.w, z[2], z[3]);
-}
-
-// VEC normals for global elements [e, e+VEC)
-template <int VEC> __device__ __forceinline__ void normal_vec(uint64_t e, uint64_t tensor_id, uint32_t k0, uint32_t k1, float (&z)[VEC])
-{
-    if constexpr (VEC == 1) {
-        float q[4];
-        normal4(e >> 2, tensor_id, k0, k1, q);
-        const int lane = (int)(e & 3);
-        z[0] = lane == 0 ? q[0] : lane == 1 ? q[1] : lane == 2 ? q[2] : q[3];
-    } else {
-#pragma unroll
-        for (int j = 0; j < VEC / 4; ++j) {
-            float q[4];
-            normal4((e >> 2) + j, tensor_id, k0, k1, q);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) z[4 * j + i] = q[i];
-        }
-    }
-}
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // the fused step
 // ------------------------------------------------------------------------------------------
-template <int CAP> struct TermTable {
-    const void *ptr[CAP];
-    float c[CAP];
-};
-
 struct StepArgs {
     int64_t nvec; // vectors of VEC elements
     int64_t per_sample, out_sample_stride;
@@ -317,23 +93,15 @@ struct StepArgs {
     void *gen_dst[NI_MAX_GEN];
     uint64_t gen_tid[NI_MAX_GEN];
     uint64_t elem_offset;
+    const uint64_t *elem_offset_dev;
     float gen_c[NI_MAX_GEN];
     float a, b0, b1, c_x0, c_xin, bias, px_scale, px_shift;
     uint8_t *pixels;
     int px_channels;
-    uint32_t k0, k1;
+    PhiloxKeys keys;
     int n_terms, n_gen;
     int has_x0, out_strided, accumulate, lp_dtype;
 };
-
-// acc += c * (VEC elements of T)
-template <typename T, int VEC> __device__ __forceinline__ void fma_term(float (&acc)[VEC], const Raw<T, VEC> &r, float c)
-{
-    float f[VEC];
-    unpack<T, VEC>(r, f);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, f[i], acc[i]);
-}
 
 // Everything after the stored terms are summed (shared by the LDG and the TMA kernels so both produce the same bits):
 // generated noise, x0 conversion + ring store, x_{k+1} store(s), per-sample sum of squares.
@@ -342,9 +110,10 @@ __device__ __forceinline__ void step_epilogue(const StepArgs &s, int64_t e, int6
                                               const Raw<TO, VEC> &ro1, const Raw<T, VEC> &rx, bool has_x0, bool has_x, bool has_o1)
 {
     // generated noise (pure ALU; overlaps loads still in flight)
+    const uint64_t eoff = s.n_gen > 0 ? effective_offset(s.elem_offset, s.elem_offset_dev) : 0;
     for (int g = 0; g < s.n_gen; ++g) {
         float z[VEC];
-        normal_vec<VEC>(s.elem_offset + (uint64_t)e, s.gen_tid[g], s.k0, s.k1, z);
+        normal_vec<VEC>(eoff + (uint64_t)e, s.gen_tid[g], s.keys, z);
         if (s.gen_dst[g] != nullptr) {
             store_raw<T, VEC>(static_cast<T *>(s.gen_dst[g]) + e, pack<T, VEC>(z));
 #pragma unroll
@@ -438,12 +207,11 @@ template <typename T, typename TO, int VEC, int CAP, bool STREAM>
 __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
     constexpr int POL = STREAM ? NI_STREAM_LOAD_POLICY : NI_LOAD_POLICY;
-    // PDL: let the next grid start launching now; do not touch global memory before the previous grid is complete
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_launch_dependents();
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
     if (v >= s.nvec) return;
     const int64_t e = v * VEC; // first element of this thread
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
 
     // issue the x0-stage loads (consumed after the term loop)
     Raw<T, VEC> rx;
@@ -722,13 +490,28 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant
 // noise only, and the pixel output stage
 // ------------------------------------------------------------------------------------------
 template <typename T, int VEC>
-__global__ void __launch_bounds__(NI_BLOCK) ni_normal_kernel(T *dst, int64_t nvec, uint32_t k0, uint32_t k1, uint64_t tensor_id, uint64_t elem_offset)
+__global__ void __launch_bounds__(NI_BLOCK) ni_normal_kernel(T *dst, int64_t nvec, const __grid_constant__ PhiloxKeys keys, uint64_t tensor_id, uint64_t elem_offset,
+                                                             const uint64_t *elem_offset_dev)
 {
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
     if (v >= nvec) return;
     float z[VEC];
-    normal_vec<VEC>(elem_offset + (uint64_t)(v * VEC), tensor_id, k0, k1, z);
+    normal_vec<VEC>(effective_offset(elem_offset, elem_offset_dev) + (uint64_t)(v * VEC), tensor_id, keys, z);
     store_raw<T, VEC>(dst + v * VEC, pack<T, VEC>(z));
+}
+
+// counter += delta (the Philox element offset of a captured graph; one thread)
+__global__ void ni_counter_add_kernel(uint64_t *counter, uint64_t delta) { *counter += delta; }
+
+// the Box-Muller transform of the noise contract on caller-chosen Philox words (edge-case tests)
+__global__ void __launch_bounds__(NI_BLOCK) ni_box_muller_kernel(const uint32_t *ra, const uint32_t *rb, float *za, float *zb, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    float a, b;
+    box_muller(ra[i], rb[i], a, b);
+    za[i] = a;
+    zb[i] = b;
 }
 
 // NCHW -> NHWC uint8.  One thread per (n, h, w) pixel reads C planes (coalesced along w) and
@@ -753,50 +536,11 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_pixel_kernel(const T *__restrict_
 // host side
 // ------------------------------------------------------------------------------------------
 
-int check_launch(const char *what)
-{
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return fail(NI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return NI_OK;
-}
-
 // Launch with programmatic dependent launch (PDL): the kernel calls griddepcontrol.launch_dependents at its top and
 // griddepcontrol.wait before its first global access, so the next ni_step's CTAs are already resident and parked
 // when this grid drains -- back-to-back steps (CUDA-graph replay, small tensors) lose no launch bubble.  After a
 // kernel that never triggers (a torch denoiser kernel) it degrades to ordinary stream order.
-template <typename Kern, typename... Args> void launch_pdl(Kern kern, unsigned blocks, cudaStream_t st, const Args &...args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(NI_BLOCK);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_pdl.load() ? 1 : 0;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
-struct DevInfo { int sms; int64_t l2_bytes; };
-
-const DevInfo &dev_info()
-{
-    static thread_local int cached_dev = -1;
-    static thread_local DevInfo info = {148, 126 << 20};
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev) {
-        int sms = 0, l2 = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
-        info.sms = sms > 0 ? sms : 148;
-        info.l2_bytes = l2 > 0 ? l2 : (126 << 20);
-        cached_dev = dev;
-    }
-    return info;
-}
+// (ni::launch_pdl in ni_common.cuh.)
 
 // Which load flavour a launch gets.  What the L2 can usefully keep between steps is what this launch WRITES (x_{k+1},
 // x0_k, kept noise: the next step and the denoiser read them first).  L2-friendly loads keep those lines resident (the
@@ -828,11 +572,11 @@ int launch_step_pol(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
         TermTable<32> tab;
         memset(&tab, 0, sizeof(tab));
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        launch_pdl(ni_step_kernel<T, TO, VEC, 32, STREAM>, blocks, st, a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, 32, STREAM>, blocks, NI_BLOCK, 0, st, opt_pdl() != 0, a, tab);
     } else {
         static thread_local TermTable<NI_MAX_TERMS> tab;
         for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-        launch_pdl(ni_step_kernel<T, TO, VEC, NI_MAX_TERMS, STREAM>, blocks, st, a, tab);
+        launch_pdl(ni_step_kernel<T, TO, VEC, NI_MAX_TERMS, STREAM>, blocks, NI_BLOCK, 0, st, opt_pdl() != 0, a, tab);
     }
     return check_launch("ni_step launch");
 }
@@ -915,6 +659,11 @@ template <typename T, typename TO> int launch_step(StepArgs &a, const NiStepDesc
         }
     }
     if (vec_ok) {
+        if (g_variant.load() == 0) { // the specialised kernels (ni_step_lean.cu) take every launch they are built for
+            bool used = false;
+            const int rc = launch_step_lean<T, TO>(d, a.x_in, launch_streams(d), st, &used);
+            if (rc != NI_OK || used) return rc;
+        }
         a.nvec = d->numel / VEC;
         return launch_step_cap<T, TO, VEC>(a, d, st);
     }
@@ -923,12 +672,16 @@ template <typename T, typename TO> int launch_step(StepArgs &a, const NiStepDesc
 }
 
 } // namespace
+} // namespace ni
+
+using namespace ni;
 
 extern "C" {
 
 int ni_version(void) { return NI_ABI_VERSION; }
 const char *ni_last_error(void) { return g_err; }
 int64_t ni_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int64_t ni_lean_launch_count(void) { return g_lean_launches.load(std::memory_order_relaxed); }
 
 int ni_set_option(const char *name, int value)
 {
@@ -993,15 +746,15 @@ int ni_step(const NiStepDesc *d, void *stream)
     a.x0_dst = d->x0_dst; a.x_next = d->x_next; a.x_next_lp = d->x_next_lp; a.sumsq = d->sumsq;
     a.a = d->a; a.b0 = d->b0; a.b1 = d->b1; a.c_x0 = d->c_x0; a.c_xin = d->has_x0 ? d->c_xin : 0.f;
     a.bias = d->bias; a.pixels = d->pixels_u8; a.px_scale = d->px_scale; a.px_shift = d->px_shift; a.px_channels = d->px_channels;
-    a.k0 = (uint32_t)d->philox_seed; a.k1 = (uint32_t)(d->philox_seed >> 32);
-    a.elem_offset = d->elem_offset;
+    a.keys = philox_keys(d->philox_seed);
+    a.elem_offset = d->elem_offset; a.elem_offset_dev = d->elem_offset_dev;
     a.n_terms = d->n_terms; a.n_gen = d->n_gen;
     a.has_x0 = d->has_x0; a.accumulate = d->accumulate; a.lp_dtype = d->lp_dtype;
     for (int g = 0; g < d->n_gen; ++g) { a.gen_tid[g] = d->gen_tensor_ids[g]; a.gen_c[g] = d->gen_coeffs[g]; a.gen_dst[g] = d->gen_dst[g]; }
 
     // 128-bit path needs every pointer 16 B aligned (8 B for half outputs next to fp32 state) and vector-sized shapes
     const int VEC = 16 / ds;
-    bool vec_ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && (d->x_next == nullptr || aligned16(d->x_next)) && (d->n_gen == 0 || d->elem_offset % 4 == 0);
+    bool vec_ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && (d->x_next == nullptr || aligned16(d->x_next));
     if (d->pixels_u8 != nullptr) vec_ok = vec_ok && (d->per_sample / d->px_channels) % VEC == 0; // a vector must stay inside one channel plane
     if (d->has_x0) {
         const uintptr_t omask = (uintptr_t)(VEC * dtype_size(od) - 1);
@@ -1082,30 +835,54 @@ int ni_weighted_sum(const void *const *src, const double *coeffs, int n_terms, v
     return fail(NI_ERR_DTYPE, "ni_weighted_sum: (src=%d, dst=%d) not built", src_dtype, dst_dtype);
 }
 
-int ni_philox_normal(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, void *stream)
+static int philox_normal_impl(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, const uint64_t *elem_offset_dev, void *stream)
 {
     if (numel == 0) return NI_OK;
     if (dst == nullptr || numel < 0) return fail(NI_ERR_INVALID, "ni_philox_normal: bad arguments");
     const int ds = dtype_size(dst_dtype);
     if (!(dst_dtype == NI_F32 || dst_dtype == NI_F16 || dst_dtype == NI_BF16)) return fail(NI_ERR_DTYPE, "ni_philox_normal: dtype %d not supported", dst_dtype);
-    if (numel == 0) return NI_OK;
     const int VEC = 16 / ds;
-    const bool vec_ok = numel % VEC == 0 && aligned16(dst) && elem_offset % 4 == 0;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const bool vec_ok = numel % VEC == 0 && aligned16(dst);
+    const PhiloxKeys keys = philox_keys(seed);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t nvec = vec_ok ? numel / VEC : numel;
     const unsigned blocks = (unsigned)((nvec + NI_BLOCK - 1) / NI_BLOCK);
     if (dst_dtype == NI_F32) {
-        if (vec_ok) ni_normal_kernel<float, 4><<<blocks, NI_BLOCK, 0, st>>>((float *)dst, nvec, k0, k1, tensor_id, elem_offset);
-        else ni_normal_kernel<float, 1><<<blocks, NI_BLOCK, 0, st>>>((float *)dst, nvec, k0, k1, tensor_id, elem_offset);
+        if (vec_ok) ni_normal_kernel<float, 4><<<blocks, NI_BLOCK, 0, st>>>((float *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
+        else ni_normal_kernel<float, 1><<<blocks, NI_BLOCK, 0, st>>>((float *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
     } else if (dst_dtype == NI_F16) {
-        if (vec_ok) ni_normal_kernel<__half, 8><<<blocks, NI_BLOCK, 0, st>>>((__half *)dst, nvec, k0, k1, tensor_id, elem_offset);
-        else ni_normal_kernel<__half, 1><<<blocks, NI_BLOCK, 0, st>>>((__half *)dst, nvec, k0, k1, tensor_id, elem_offset);
+        if (vec_ok) ni_normal_kernel<__half, 8><<<blocks, NI_BLOCK, 0, st>>>((__half *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
+        else ni_normal_kernel<__half, 1><<<blocks, NI_BLOCK, 0, st>>>((__half *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
     } else {
-        if (vec_ok) ni_normal_kernel<__nv_bfloat16, 8><<<blocks, NI_BLOCK, 0, st>>>((__nv_bfloat16 *)dst, nvec, k0, k1, tensor_id, elem_offset);
-        else ni_normal_kernel<__nv_bfloat16, 1><<<blocks, NI_BLOCK, 0, st>>>((__nv_bfloat16 *)dst, nvec, k0, k1, tensor_id, elem_offset);
+        if (vec_ok) ni_normal_kernel<__nv_bfloat16, 8><<<blocks, NI_BLOCK, 0, st>>>((__nv_bfloat16 *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
+        else ni_normal_kernel<__nv_bfloat16, 1><<<blocks, NI_BLOCK, 0, st>>>((__nv_bfloat16 *)dst, nvec, keys, tensor_id, elem_offset, elem_offset_dev);
     }
     return check_launch("ni_philox_normal launch");
+}
+
+int ni_philox_normal(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, void *stream)
+{
+    return philox_normal_impl(dst, numel, dst_dtype, seed, tensor_id, elem_offset, nullptr, stream);
+}
+
+int ni_philox_normal_at(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, const uint64_t *elem_offset_dev, void *stream)
+{
+    return philox_normal_impl(dst, numel, dst_dtype, seed, tensor_id, elem_offset, elem_offset_dev, stream);
+}
+
+int ni_counter_add(uint64_t *counter_dev, uint64_t delta, void *stream)
+{
+    if (counter_dev == nullptr) return fail(NI_ERR_INVALID, "ni_counter_add: NULL counter");
+    ni_counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter_dev, delta);
+    return check_launch("ni_counter_add launch");
+}
+
+int ni_debug_box_muller(const uint32_t *ra, const uint32_t *rb, float *za, float *zb, int64_t n, void *stream)
+{
+    if (n == 0) return NI_OK;
+    if (ra == nullptr || rb == nullptr || za == nullptr || zb == nullptr || n < 0) return fail(NI_ERR_INVALID, "ni_debug_box_muller: bad arguments");
+    ni_box_muller_kernel<<<(unsigned)((n + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, static_cast<cudaStream_t>(stream)>>>(ra, rb, za, zb, n);
+    return check_launch("ni_debug_box_muller launch");
 }
 
 int ni_to_pixel_u8(const void *x, int src_dtype, uint8_t *dst, int64_t batch, int channels, int height, int width, float scale, float shift, void *stream)

@@ -39,3 +39,24 @@ def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
         return len(cpus)
     except OSError:
         return None
+
+
+def bind_rank_cpus(local_rank: int, local_world: int) -> Optional[int]:
+    """One process per GPU: give THIS rank its own disjoint slice of CPUs, taken from the NUMA node of its GPU and shared
+    out among the ranks whose GPUs hang off the same node (round 1 pinned all 8 ranks of a box to the same 32 CPUs, where
+    their launch threads, copy-engine callbacks and NCCL proxies competed).  Call before allocating pinned host buffers so
+    they are first-touched on the right node.  Returns the number of CPUs bound, or None if the topology is unknown."""
+    mine = gpu_local_cpus(local_rank)
+    if not mine:
+        return None
+    peers = [r for r in range(local_world) if gpu_local_cpus(r) == mine] if local_world > 1 else [local_rank]
+    cpus = sorted(mine)
+    if len(peers) > 1 and len(cpus) >= len(peers):
+        i, n = peers.index(local_rank), len(peers)
+        per = len(cpus) // n
+        cpus = cpus[i * per:(i + 1) * per]
+    try:
+        os.sched_setaffinity(0, set(cpus))
+        return len(cpus)
+    except OSError:
+        return None

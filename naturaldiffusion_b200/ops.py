@@ -60,15 +60,22 @@ def weighted_sum_tensors(coeffs: Sequence[float], tensors: Sequence[torch.Tensor
 
 
 def philox_normal(shape, *, seed: int, tensor_id: int, elem_offset: int = 0, dtype=torch.float32, device="cuda",
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, elem_offset_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """N(0,1) tensor of the noise contract (include/ni_b200.h); identical values for any sharding
-    as long as each shard passes its own global `elem_offset`."""
+    as long as each shard passes its own global `elem_offset`.  elem_offset_dev: a 1-element int64 CUDA tensor whose
+    value is added to elem_offset when the kernel runs (ni_philox_normal_at)."""
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=device)
     _require_cuda(out, "out")
     with torch.cuda.device(out.device):
-        check(_lib.lib().ni_philox_normal(out.data_ptr(), out.numel(), _code(out.dtype), seed & (2**64 - 1), tensor_id,
-                                          elem_offset, stream_ptr(out.device)), "ni_philox_normal")
+        if elem_offset_dev is None:
+            check(_lib.lib().ni_philox_normal(out.data_ptr(), out.numel(), _code(out.dtype), seed & (2**64 - 1), tensor_id,
+                                              elem_offset, stream_ptr(out.device)), "ni_philox_normal")
+        else:
+            if not elem_offset_dev.is_cuda or elem_offset_dev.dtype != torch.int64 or elem_offset_dev.numel() != 1:
+                raise NiError("elem_offset_dev must be a 1-element int64 CUDA tensor")
+            check(_lib.lib().ni_philox_normal_at(out.data_ptr(), out.numel(), _code(out.dtype), seed & (2**64 - 1), tensor_id,
+                                                 elem_offset, elem_offset_dev.data_ptr(), stream_ptr(out.device)), "ni_philox_normal_at")
     return out
 
 
@@ -94,7 +101,7 @@ class StepLaunch:
     def __init__(self, *, numel, per_sample, dtype, out_dtype=None, has_x0=True, x_in=0, out0=0, out1=0,
                  out_sample_stride=None, a=0.0, b0=0.0, b1=0.0, x0_dst=0, c_x0=0.0, c_xin=0.0,
                  terms=(), gens=(), seed=0, elem_offset=0, accumulate=False, x_next=0, x_next_lp=0, lp_dtype=NI_BF16, sumsq=0,
-                 bias=0.0, pixels_u8=0, px_scale=0.5, px_shift=0.5, px_channels=0):
+                 bias=0.0, pixels_u8=0, px_scale=0.5, px_shift=0.5, px_channels=0, elem_offset_dev=0):
         """terms: iterable of (device_ptr, coeff); gens: iterable of (tensor_id, coeff, dst_ptr_or_0)."""
         terms = list(terms)
         gens = list(gens)
@@ -126,6 +133,7 @@ class StepLaunch:
             d.gen_dst[i] = dst or None
         d.philox_seed = int(seed) & (2**64 - 1)
         d.elem_offset = int(elem_offset)
+        d.elem_offset_dev = elem_offset_dev or None
         d.accumulate = 1 if accumulate else 0
         d.x_next = x_next or None
         d.x_next_lp = x_next_lp or None

@@ -32,12 +32,19 @@ class NaturalInferenceSampler:
     def __init__(self, triple: CoeffTriple, io_scaling: Sequence[Tuple[float, float, float]], batch: int,
                  sample_shape: Sequence[int], *, device="cuda", dtype: torch.dtype = torch.float32, seed: int = 0,
                  eps0: str = "stored", lp_dtype: Optional[torch.dtype] = None, track_sumsq: bool = False,
-                 sample_offset: int = 0, keep_all_x0: bool = False, markov="auto", final_scale: float = 1.0, final_bias: float = 0.0):
+                 sample_offset: int = 0, keep_all_x0: bool = False, markov="auto", final_scale: float = 1.0, final_bias: float = 0.0,
+                 advance: Optional[int] = None):
         """
         triple       coefficient matrices (A, B, node)
         io_scaling   K tuples (a_k, b0_k, b1_k): x0_k = a_k x_k + b0_k out0 + b1_k out1 (coeffs.io_*)
         batch        samples on THIS rank; sample_offset = global index of its first sample, so the
                      Philox noise of a sharded run equals the single-GPU run
+        advance      samples the noise index moves forward after every trajectory that drew noise in-kernel (default: `batch`;
+                     a run sharded over G ranks passes G*batch so shards never overlap; 0 = repeat the same draws).  Like
+                     the reference's torch.randn / randn_like (src/ValidateNaturalInference.py:345,359) every call gets new
+                     noise -- including the fresh per-step noise of stochastic matrices when the caller supplies the initial
+                     tensor.  The index lives in a DEVICE counter read by the kernels, so a captured CUDA graph also draws
+                     new noise on each replay.
         eps0         "stored": the initial noise lives in a slot and is re-read by every row that uses it
                      "regen" : rows regenerate it in-kernel from (seed, tensor 0) -- no slot, no reads
         lp_dtype     also emit x_{k+1} in fp16/bf16 for a reduced-precision denoiser (fp32 state only)
@@ -71,7 +78,11 @@ class NaturalInferenceSampler:
         self.seed = int(seed)
         self.eps0_mode = eps0
         self.lp_dtype = lp_dtype
-        self.elem_offset = int(sample_offset) * self.per_sample
+        self.advance = self.batch if advance is None else int(advance)
+        # the Philox element offset of this shard: a device counter (all descriptors carry its address, their host offset is 0)
+        self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._graphs = {}
+        self.set_sample_offset(sample_offset)
         self.final_scale, self.final_bias = float(final_scale), float(final_bias)
         from .coeffs import markov_ratios
         use_markov = (markov_ratios(triple) is not None) if markov == "auto" else bool(markov)
@@ -89,22 +100,22 @@ class NaturalInferenceSampler:
         self._launches: Optional[List[List[StepLaunch]]] = None
         self._launch_key = None
         self._launch_cache = {}
-        self._graph = None
-        self._graph_out = None
         self.kernel_launches_per_trajectory = sum(p.launches(k, eps0 == "stored") for k in range(self.K))
 
     def set_sample_offset(self, sample_offset: int):
-        """Re-target this sampler at another batch of a larger run: batch `[sample_offset, sample_offset + B)` of the
-        global sample index space.  In-kernel noise is keyed by the global element index, so a run split into batches
-        (or ranks) of any size draws the same samples."""
-        off = int(sample_offset) * self.per_sample
-        if off != self.elem_offset:
-            self.elem_offset = off
-            for launches in self._launch_cache.values():  # prepared descriptors stay valid: only the Philox index moves
-                for row in launches:
-                    for L in row:
-                        L.desc.elem_offset = off
-            self._graph = None
+        """Re-target this sampler at batch `[sample_offset, sample_offset + B)` of the global sample index space.  In-kernel
+        noise is keyed by the global element index, so a run split into batches (or ranks) of any size draws the same
+        samples.  Stream-ordered (a device fill); prepared descriptors and captured graphs stay valid."""
+        self.elem_offset = int(sample_offset) * self.per_sample  # host mirror of the device counter
+        with torch.cuda.device(self.device):
+            self._counter.fill_(self.elem_offset)
+
+    def _advance_noise(self, st: int):
+        """After a trajectory that drew noise in-kernel: move the device counter (inside the stream / graph) and its host mirror."""
+        if self.advance:
+            delta = self.advance * self.per_sample
+            _lib.check(_lib.lib().ni_counter_add(self._counter.data_ptr(), delta, st), "ni_counter_add")
+            self.elem_offset += delta
 
     # ------------------------------------------------------------------ views
     def full_shape(self):
@@ -162,7 +173,8 @@ class NaturalInferenceSampler:
                     c_x0, c_xin = c_x0 * fs, c_xin * fs
                 bias = self.final_bias
                 pix = pix_ptr
-            common = dict(numel=self.numel, per_sample=self.per_sample, dtype=code, seed=self.seed, elem_offset=self.elem_offset)
+            common = dict(numel=self.numel, per_sample=self.per_sample, dtype=code, seed=self.seed, elem_offset=0,
+                          elem_offset_dev=self._counter.data_ptr())
             chunks = [terms[i:i + NI_MAX_TERMS] for i in range(0, max(len(terms), 1), NI_MAX_TERMS)]
             if pix and len(chunks) == 1:
                 x_next = 0  # the uint8 image replaces x_K (a chained >512-term row still needs x_K to accumulate into)
@@ -244,7 +256,7 @@ class NaturalInferenceSampler:
                 x_init = eps0 = noise
             else:
                 tgt = self._eps0 if self.eps0_mode == "stored" else self._X[0]
-                x_init = eps0 = philox_normal(shape, seed=self.seed, tensor_id=0, elem_offset=self.elem_offset, out=tgt.view(shape))
+                x_init = eps0 = philox_normal(shape, seed=self.seed, tensor_id=0, elem_offset=0, elem_offset_dev=self._counter, out=tgt.view(shape))
             fresh_ptrs = None
             if fresh_noise is not None:
                 if len(fresh_noise) != self.K:
@@ -278,34 +290,48 @@ class NaturalInferenceSampler:
                 x = (out if (k == self.K - 1 and out is not None) else self._X[(k + 1) % 2]).view(shape)
                 if record:
                     trace.append(dict(x0=self.x0_slot(k).clone(), x_next=x.clone()))
+            if noise is None or any(L.desc.n_gen for row in self._launches for L in row):
+                self._advance_noise(st)
         if pixels_out is not None:
             return pixels_out
         return (x, trace) if record else x
 
     # ------------------------------------------------------------------ CUDA graph of the whole trajectory
     @torch.no_grad()
-    def capture(self, denoiser: Callable, noise: Optional[torch.Tensor] = None):
-        """Capture the K steps (denoiser included) in one CUDA graph.  `noise` (if given) is a static
-        input buffer the caller refills between replays; otherwise noise is generated inside the graph
-        from the sampler seed (same tensors every replay unless `self.seed` handling is external)."""
+    def capture(self, denoiser: Callable, noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                pixels_out: Optional[torch.Tensor] = None):
+        """Capture the K steps (denoiser included) in one CUDA graph.  `noise` (if given) is a static input buffer the
+        caller refills between replays; otherwise noise is generated inside the graph.  The noise index is a device counter
+        advanced INSIDE the graph, so every replay draws the next batch's noise (set_sample_offset rewinds it).  Several
+        graphs (one per buffer set) can coexist; replay() replays the last one captured, replay(g) a given one."""
         with torch.cuda.device(self.device):
+            start = self.elem_offset
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self.sample(denoiser, noise=noise)
+                    self.sample(denoiser, noise=noise, out=out, pixels_out=pixels_out)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
+            before = self.elem_offset
             with torch.cuda.graph(g):
-                res = self.sample(denoiser, noise=noise)
-            self._graph, self._graph_out = g, res
+                res = self.sample(denoiser, noise=noise, out=out, pixels_out=pixels_out)
+            g._ni_delta = self.elem_offset - before  # what one replay adds to the counter
+            g._ni_out = res
+            self._graphs[(noise.data_ptr() if noise is not None else 0, out.data_ptr() if out is not None else 0,
+                          pixels_out.data_ptr() if pixels_out is not None else 0)] = g
+            self._graph = g
+            self.elem_offset = start  # capture executed nothing; the warm-up runs are rewound
+            self._counter.fill_(start)
         return g
 
-    def replay(self) -> torch.Tensor:
-        if self._graph is None:
+    def replay(self, graph=None) -> torch.Tensor:
+        g = graph if graph is not None else getattr(self, "_graph", None)
+        if g is None:
             raise NiError("capture() first")
-        self._graph.replay()
-        return self._graph_out
+        g.replay()
+        self.elem_offset += g._ni_delta
+        return g._ni_out
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end)
     @torch.no_grad()
@@ -316,7 +342,9 @@ class NaturalInferenceSampler:
         shape = self.full_shape()
         if noise_host.device.type != "cpu" or noise_host.shape != shape or noise_host.dtype != self.dtype:
             raise NiError("noise_host must be a CPU tensor matching the state shape/dtype")
-        dev_noise = self._eps0.view(shape) if self.eps0_mode == "stored" else self._X[0].view(shape)
+        # always staged in the eps_0 slot (never in the X ping-pong buffers, which step 1 overwrites while later rows
+        # still read eps_0 through this pointer)
+        dev_noise = self._eps0.view(shape)
         dev_noise.copy_(noise_host, non_blocking=True)
         if pixels:
             if not hasattr(self, "_pix"):
@@ -328,16 +356,17 @@ class NaturalInferenceSampler:
         out_host.copy_(x, non_blocking=True)
         return out_host
 
-
     @torch.no_grad()
     def sample_host_many(self, denoiser: Callable, noise_hosts: Optional[Sequence[torch.Tensor]], out_hosts: Sequence[torch.Tensor],
-                         pixels: bool = False, first_sample: int = 0):
+                         pixels: bool = False, first_sample: Optional[int] = None, graph: bool = False):
         """Pipelined end-to-end over many batches with HOST buffers (the reference generates 100 batches of 500,
         src/CIFAR10NaturalInference.py:288-309): the H2D copy of batch i+1 and the D2H copy of batch i-1 run on
         their own streams while batch i computes; two device staging buffers per direction.  Returns after
         enqueueing everything; the caller synchronises (torch.cuda.synchronize or the returned event).
         noise_hosts=None: like the reference, draw the noise on the device (in-kernel Philox keyed by the global sample
-        index first_sample + i*B) -- nothing but the results crosses PCIe."""
+        index) -- nothing but the results crosses PCIe.  first_sample (optional) rewinds the noise index first; batch i
+        then draws samples [first_sample + i*advance, + B).  graph=True replays one captured CUDA graph per batch (two
+        graphs, one per staging-buffer parity) instead of K ctypes launches: the denoiser must be capturable."""
         n = len(out_hosts)
         if noise_hosts is not None and len(noise_hosts) != n:
             raise NiError("need one output buffer per noise batch")
@@ -348,11 +377,20 @@ class NaturalInferenceSampler:
             self._stage = dict(
                 noise=[torch.empty(shape, dtype=self.dtype, device=dev) for _ in range(2)],
                 out=[(torch.empty((b, h, w, c), dtype=torch.uint8, device=dev) if pixels else torch.empty(shape, dtype=self.dtype, device=dev)) for _ in range(2)],
-                pixels=pixels, h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev))
+                pixels=pixels, h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev), graphs={})
         st = self._stage
         if st["pixels"] != pixels:
             raise NiError("sample_host_many was first used with a different `pixels` setting on this sampler")
+        if first_sample is not None:
+            self.set_sample_offset(first_sample)
         main = torch.cuda.current_stream(dev)
+        if graph:
+            for par in range(min(2, n)):
+                key = (par, noise_hosts is not None, id(denoiser))
+                if key not in st["graphs"]:
+                    nb = st["noise"][par] if noise_hosts is not None else None
+                    kw = dict(pixels_out=st["out"][par]) if pixels else dict(out=st["out"][par])
+                    st["graphs"][key] = (self.capture(denoiser, noise=nb, **kw), denoiser)  # keeps the denoiser alive with its graph
         c_done, d_done = [None] * n, [None] * n
         for i in range(n):
             nb, ob = st["noise"][i % 2], st["out"][i % 2]
@@ -370,11 +408,12 @@ class NaturalInferenceSampler:
                     h_done.record(st["h2d"])
                 main.wait_event(h_done)
             else:
-                self.set_sample_offset(first_sample + i * self.batch)
                 nb = None
             if i >= 2:
                 main.wait_event(d_done[i - 2])                # batch i-2's result has left this output buffer
-            if pixels:
+            if graph:
+                self.replay(st["graphs"][(i % 2, noise_hosts is not None, id(denoiser))][0])
+            elif pixels:
                 self.sample(denoiser, noise=nb, pixels_out=ob)
             else:
                 self.sample(denoiser, noise=nb, out=ob)

@@ -21,8 +21,17 @@ def lib():
         L.ni_oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.ni_oracle_philox_normal_f32.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_uint64]
         L.ni_oracle_weighted_sum_f32.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.c_int, C.c_void_p, C.c_int64]
+        L.ni_oracle_box_muller.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _lib = L
     return _lib
+
+
+def box_muller(ra: np.ndarray, rb: np.ndarray):
+    """(za, zb) of the noise contract for Philox words (ra, rb), evaluated in fp64 and rounded to fp32"""
+    ra, rb = np.ascontiguousarray(ra, dtype=np.uint32), np.ascontiguousarray(rb, dtype=np.uint32)
+    za, zb = np.empty(ra.shape, dtype=np.float32), np.empty(ra.shape, dtype=np.float32)
+    lib().ni_oracle_box_muller(ra.ctypes.data, rb.ctypes.data, za.ctypes.data, zb.ctypes.data, ra.size)
+    return za, zb
 
 
 def philox4x32_10(ctr, key):

@@ -58,6 +58,12 @@ static void box_muller(uint32_t ra, uint32_t rb, float *za, float *zb)
     *zb = (float)(rad * sin(PI * (double)v));
 }
 
+/* the transform alone, on caller-chosen Philox words (edge cases: u -> 1, u -> 2^-33, the tails) */
+void ni_oracle_box_muller(const uint32_t *ra, const uint32_t *rb, float *za, float *zb, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) box_muller(ra[i], rb[i], &za[i], &zb[i]);
+}
+
 /* dst[i] = N(0,1) sample of global element elem_offset+i of noise tensor `tensor_id`. */
 void ni_oracle_philox_normal_f32(float *dst, int64_t numel, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset)
 {

@@ -21,8 +21,26 @@ import types
 REF_ROOT = os.environ.get("NI_REFERENCE_ROOT", "/root/reference")
 
 
-def available() -> bool:
+def present() -> bool:
+    """the reference tree exists (reading it as TEXT is always allowed: signatures(), the shipped matrices)"""
     return os.path.isfile(os.path.join(REF_ROOT, "src", "ValidateNaturalInference.py"))
+
+
+def available() -> bool:
+    """EXECUTING reference code is opt-in: the tree is untrusted public content, and importing it leaves stubbed
+    ``sys.modules`` entries and ``sys.path`` edits behind while it runs.  Only ``tests/golden/make_golden.py`` (which
+    sets NI_EXEC_REFERENCE=1 itself) and a developer who exports the flag get the exec-based loaders; default test
+    runs rely on the committed goldens."""
+    return present() and os.environ.get("NI_EXEC_REFERENCE", "") == "1"
+
+
+def signatures(relpath: str) -> dict:
+    """{function name: [parameter names]} of the top-level functions of a reference source file, by PARSING it
+    (ast) -- nothing is executed."""
+    import ast
+    with open(os.path.join(REF_ROOT, relpath)) as f:
+        tree = ast.parse(f.read())
+    return {n.name: [a.arg for a in n.args.args] for n in tree.body if isinstance(n, ast.FunctionDef)}
 
 
 class _Stub(types.ModuleType):

@@ -20,7 +20,7 @@ from naturaldiffusion_b200.adapters import ncsnpp_denoiser  # noqa: E402
 from naturaldiffusion_b200.denoisers import NCSNppVP  # noqa: E402
 from naturaldiffusion_b200.sampler import NaturalInferenceSampler  # noqa: E402
 
-W = os.path.join(ROOT, "tests", "golden", "reference_weights")
+W = os.path.join(ROOT, "naturaldiffusion_b200", "data", "weights")
 
 
 def reference_eager_loop(A, B, node, model, noise):

@@ -9,7 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-WEIGHTS = os.path.join(GOLDEN, "reference_weights")
+WEIGHTS = os.path.join(ROOT, "naturaldiffusion_b200", "data", "weights")  # the shipped coefficient inputs of the path
 
 
 def pytest_configure(config):

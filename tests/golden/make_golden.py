@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+os.environ["NI_EXEC_REFERENCE"] = "1"  # generating fixtures is the one place that executes reference code
 from oracle import ref_loader  # noqa: E402
 from toy_models import ToyEps  # noqa: E402
 
@@ -166,7 +167,7 @@ def gen_sd3():
 def gen_weights():
     """The shipped inputs of the hot path (weights/*.npz, weights/*.csv): re-saved array by array / line by line so the
     fixtures carry exactly the reference's numbers (positional npz order kept: xstart, epsilon, node)."""
-    out_dir = os.path.join(HERE, "reference_weights")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(HERE)), "naturaldiffusion_b200", "data", "weights")
     os.makedirs(out_dir, exist_ok=True)
     for f in sorted(glob.glob(os.path.join(REF, "weights", "*.npz"))):
         with np.load(f) as z:

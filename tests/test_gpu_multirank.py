@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 pytestmark = pytest.mark.gpu
-WEIGHTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_weights")
+WEIGHTS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "naturaldiffusion_b200", "data", "weights")
 
 
 def _free_port():

@@ -440,21 +440,43 @@ def test_shard_range_partitions():
 
 
 def test_dropins_fit_the_reference_modules():
-    """(build container only) the real reference script modules expose exactly the names `dropin.install` replaces, with
-    call signatures the replacements accept"""
+    """(build container only) the reference scripts define exactly the names `dropin.install` replaces, with call
+    signatures the replacements accept.  The reference sources are PARSED (ast), not executed."""
     import inspect
+    import types
     from oracle import ref_loader
-    if not ref_loader.available():
+    if not ref_loader.present():
         pytest.skip("reference tree not present (GPU box)")
     from naturaldiffusion_b200 import dropin
-    v, s3 = ref_loader.validate_module(), ref_loader.sd3_module()
-    data_fn, wsum = ref_loader.cifar_functions()
-    assert list(inspect.signature(v.weighted_sum).parameters) == ["weights", "seq_elem"]
-    assert list(inspect.signature(wsum).parameters) == ["past_x0_coeff", "seq_x0"]
-    assert list(inspect.signature(s3.weighted_sum).parameters) == ["seq_xstarts", "weights"]
-    assert list(inspect.signature(s3.euler_weighted_sum).parameters) == ["seq_xstarts", "cliplen"]
-    assert list(inspect.signature(data_fn).parameters) == list(inspect.signature(dropin.data_fn).parameters)
+    v = ref_loader.signatures("src/ValidateNaturalInference.py")
+    s3 = ref_loader.signatures("src/SD3NaturalInference.py")
+    cf = ref_loader.signatures("src/CIFAR10NaturalInference.py")
+    assert v["weighted_sum"] == ["weights", "seq_elem"]
+    assert cf["weighted_sum"] == ["past_x0_coeff", "seq_x0"]
+    assert s3["weighted_sum"] == ["seq_xstarts", "weights"]
+    assert s3["euler_weighted_sum"] == ["seq_xstarts", "cliplen"]
+    assert cf["data_fn"] == list(inspect.signature(dropin.data_fn).parameters)
     assert len(inspect.signature(dropin.weighted_sum).parameters) == 2
     assert list(inspect.signature(dropin.euler_weighted_sum).parameters) == ["seq_xstarts", "cliplen"]
-    assert set(dropin.install(v)) == {"weighted_sum"} and v.weighted_sum is dropin.weighted_sum
-    assert set(dropin.install(s3)) == {"weighted_sum", "euler_weighted_sum"}
+    # install() patches exactly the hot-path names a module defines
+    mv = types.SimpleNamespace(**{k: None for k in v})
+    ms = types.SimpleNamespace(**{k: None for k in s3})
+    mc = types.SimpleNamespace(**{k: None for k in cf})
+    assert set(dropin.install(mv)) == {"weighted_sum"} and mv.weighted_sum is dropin.weighted_sum
+    assert set(dropin.install(ms)) == {"weighted_sum", "euler_weighted_sum"}
+    assert set(dropin.install(mc)) == {"weighted_sum", "data_fn"}
+
+
+def test_kxk_epsilon_matrix_uses_column_zero_only():
+    """weights/*.npz carry a K x K past_epsilon_coeff whose reader uses column 0 only (src/CIFAR10NaturalInference.py:303)"""
+    import warnings
+    K = 4
+    A = np.tril(np.ones((K, K)))
+    B = np.zeros((K, K)); B[:, 0] = 0.5; B[2, 1] = 0.25
+    node = np.stack([np.linspace(1, 0, K + 1)] * 3, axis=1)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        t = CoeffTriple(A, B, node)
+    assert w and "column 0" in str(w[0].message)
+    assert t.B.shape == (K, K + 1) and np.all(t.B[:, 0] == 0.5) and np.all(t.B[:, 1:] == 0)
+    assert all(s.fresh is None for s in build_plan(t).steps)
