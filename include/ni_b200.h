@@ -162,6 +162,14 @@ int ni_debug_box_muller(const uint32_t *ra, const uint32_t *rb, float *za, float
 int ni_to_pixel_u8(const void *x, int src_dtype, uint8_t *dst_nhwc, int64_t batch, int channels,
                    int height, int width, float scale, float shift, void *stream);
 
+/* FID sufficient statistics (the evaluation step that follows sampling).  The reference computes
+ * mu = np.mean(act, 0), sigma = np.cov(act, rowvar=False) over all pool3 activations on the host
+ * (src/CIFAR10NaturalInference.py:73-86).  Here each rank accumulates  stats = [n | sum x (d) | sum x x^T (d*d, row-major)]
+ * in fp64 on its GPU -- feats is [m, d] fp32 with row pitch ld (elements), widened in registers; the rank-k update runs on the
+ * fp64 tensor cores (DMMA), upper triangle computed once and mirrored, deterministic -- and one all-reduce of `stats` merges
+ * the ranks.  stats += (this batch); the caller zeroes it once. */
+int ni_fid_accumulate(const float *feats, int64_t m, int d, int64_t ld, double *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

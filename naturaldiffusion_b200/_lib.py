@@ -99,6 +99,8 @@ def lib():
     L.ni_counter_add.restype = C.c_int
     L.ni_debug_box_muller.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.ni_debug_box_muller.restype = C.c_int
+    L.ni_fid_accumulate.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ni_fid_accumulate.restype = C.c_int
     L.ni_to_pixel_u8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_float, C.c_void_p]
     L.ni_to_pixel_u8.restype = C.c_int
@@ -110,7 +112,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ("ni_version", "ni_last_error", "ni_launch_count", "ni_lean_launch_count", "ni_set_option", "ni_step", "ni_step_flavour",
                     "ni_weighted_sum", "ni_philox_normal", "ni_philox_normal_at", "ni_counter_add", "ni_debug_box_muller",
-                    "ni_to_pixel_u8")
+                    "ni_to_pixel_u8", "ni_fid_accumulate")
 
 
 def check(rc: int, what: str = "libni_b200"):

@@ -22,13 +22,26 @@ class FidAccumulator:
 
     @property
     def n(self) -> float:
+        """sample count so far (reads the device buffer: synchronises; call it after the loop, not inside it)"""
         return float(self.buf[0])
 
     @torch.no_grad()
     def update(self, feats: torch.Tensor):
-        """feats: [m, dim] activations (any float dtype) of this rank's samples."""
+        """feats: [m, dim] activations of this rank's samples.  On a CUDA accumulator this is ONE call of
+        `ni_fid_accumulate` (csrc/ni_fid.cu: fp32 activations widened in registers, fp64 tensor-core rank-k update, column
+        sums, count) on the current stream -- no fp64 copy of the activations, no sync.  A CPU accumulator (the gloo
+        host-logic tests) uses plain torch."""
         if feats.dim() != 2 or feats.shape[1] != self.dim:
             raise ValueError(f"expected [m, {self.dim}] features, got {tuple(feats.shape)}")
+        if self.device.type == "cuda":
+            from . import _lib
+            f = feats.to(self.device, torch.float32)
+            if f.stride(1) != 1 or f.stride(0) % 4 != 0 or f.data_ptr() % 16 != 0:
+                f = f.contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().ni_fid_accumulate(f.data_ptr(), f.shape[0], self.dim, f.stride(0) if f.shape[0] > 1 else self.dim,
+                                                        self.buf.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream), "ni_fid_accumulate")
+            return self
         f = feats.to(self.device, torch.float64)
         self.buf[0] += f.shape[0]
         self.buf[1:1 + self.dim] += f.sum(0)

@@ -70,13 +70,6 @@ def flow_euler_triple(num_step: int, sigmas=None) -> CoeffTriple:
     return first_order_triple(p, 1 - p, None, node, name=f"flow_euler_{num_step:03d}")
 
 
-def markov_ratio(triple: CoeffTriple, tol: float = 1e-12):
-    """see coeffs.markov_ratios (kept here for discoverability next to the generators)"""
-    from .coeffs import markov_ratios
-    mr = markov_ratios(triple, tol)
-    return None if mr is None else np.array(mr[0])
-
-
 # ----------------------------------------------------------------------------------------------
 # any linear sampler -> matrices, by running it in coefficient space (SURVEY appendix D.15)
 # ----------------------------------------------------------------------------------------------
@@ -330,6 +323,330 @@ def dpm_solver_3s_triple(steps: int, plus_plus: bool = False, t_T=1.0, t_0=1e-3)
             x = (np.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - ns.sigma(t) * np.expm1(h) * e_s
                  - (1.0 / r2) * ns.sigma(t) * (np.expm1(h) / h - 1.0) * (e_s2 - e_s))
     return tr.finish(x, ts[-1], name=("dpmsolverpp3s" if plus_plus else "dpmsolver3s") + f"_{3 * steps:03d}")
+
+
+# ----------------------------------------------------------------------------------------------
+# DPM-Solver / DPM-Solver++ exactly as the reference drives them for results/FID/dpmsolver*_{5,10,15}step.csv
+# (src/CIFAR10NaturalInference.py:363-393: multistep | singlestep, order 2 | 3, time_quadratic, lower_order_final=False)
+# ----------------------------------------------------------------------------------------------
+def solver_time_steps(skip_type: str, t_T: float, t_0: float, N: int, ns: "VPLinearSchedule" = None):
+    """`DPM_Solver.get_time_steps` (deps/dpm_solver_pytorch.py:455-482), float64."""
+    if skip_type == "time_uniform":
+        return np.linspace(t_T, t_0, N + 1)
+    if skip_type == "time_quadratic":
+        return np.linspace(t_T ** 0.5, t_0 ** 0.5, N + 1) ** 2
+    if skip_type == "logSNR":
+        ns = ns or VPLinearSchedule()
+        return ns.inv_lam(np.linspace(ns.lam(t_T), ns.lam(t_0), N + 1))
+    raise ValueError(f"unsupported skip_type {skip_type!r}")
+
+
+def singlestep_orders(steps: int, order: int):
+    """order of every outer step so that the model calls add up to `steps` (deps/dpm_solver_pytorch.py:514-533)"""
+    if order == 3:
+        K = steps // 3 + 1
+        return [3] * (K - 2) + [2, 1] if steps % 3 == 0 else [3] * (K - 1) + ([1] if steps % 3 == 1 else [2])
+    if order == 2:
+        return [2] * (steps // 2) if steps % 2 == 0 else [2] * (steps // 2) + [1]
+    if order == 1:
+        return [1] * steps
+    raise ValueError("order must be 1, 2 or 3")
+
+
+class _DpmUpdates:
+    """The six update formulas of deps/dpm_solver_pytorch.py (solver_type 'dpmsolver') on coefficient vectors.  `pp`
+    selects data prediction (DPM-Solver++, model value = x0) or noise prediction (DPM-Solver, model value = eps)."""
+
+    def __init__(self, ns, pp: bool, tracer: "CoefficientTracer"):
+        self.ns, self.pp, self.tr = ns, pp, tracer
+
+    def model(self, x, t):
+        return self.tr.model_x0(x, t) if self.pp else self.tr.model_eps(x, t)
+
+    def _lin(self, s, t):
+        """(coefficient of x, coefficient scale of the model value, h) of a step s -> t"""
+        ns = self.ns
+        h = ns.lam(t) - ns.lam(s)
+        if self.pp:
+            return ns.sigma(t) / ns.sigma(s), ns.alpha(t), h
+        return np.exp(ns.log_alpha(t) - ns.log_alpha(s)), ns.sigma(t), h
+
+    def _phi1(self, h):
+        return np.expm1(-h) if self.pp else np.expm1(h)
+
+    def first(self, x, s, t, m_s):                                   # :547-592
+        cx, cm, h = self._lin(s, t)
+        return cx * x - cm * self._phi1(h) * m_s
+
+    def single_second(self, x, s, t, r1):                            # :594-676
+        ns = self.ns
+        m_s = self.model(x, s)
+        h = ns.lam(t) - ns.lam(s)
+        s1 = ns.inv_lam(ns.lam(s) + r1 * h)
+        x_s1 = self.first(x, s, s1, m_s)
+        m_s1 = self.model(x_s1, s1)
+        cx, cm, _ = self._lin(s, t)
+        phi_1 = self._phi1(h)
+        return cx * x - cm * phi_1 * m_s - (0.5 / r1) * cm * phi_1 * (m_s1 - m_s)
+
+    def single_third(self, x, s, t, r1, r2):                         # :677-795
+        ns = self.ns
+        m_s = self.model(x, s)
+        h = ns.lam(t) - ns.lam(s)
+        s1, s2 = ns.inv_lam(ns.lam(s) + r1 * h), ns.inv_lam(ns.lam(s) + r2 * h)
+        x_s1 = self.first(x, s, s1, m_s)
+        m_s1 = self.model(x_s1, s1)
+        cx2, cm2, _ = self._lin(s, s2)
+        cx, cm, _ = self._lin(s, t)
+        if self.pp:
+            phi_12, phi_1 = np.expm1(-r2 * h), np.expm1(-h)
+            phi_22, phi_2 = phi_12 / (r2 * h) + 1.0, phi_1 / h + 1.0
+            x_s2 = cx2 * x - cm2 * phi_12 * m_s + (r2 / r1) * cm2 * phi_22 * (m_s1 - m_s)
+            m_s2 = self.model(x_s2, s2)
+            return cx * x - cm * phi_1 * m_s + (1.0 / r2) * cm * phi_2 * (m_s2 - m_s)
+        phi_12, phi_1 = np.expm1(r2 * h), np.expm1(h)
+        phi_22, phi_2 = phi_12 / (r2 * h) - 1.0, phi_1 / h - 1.0
+        x_s2 = cx2 * x - cm2 * phi_12 * m_s - (r2 / r1) * cm2 * phi_22 * (m_s1 - m_s)
+        m_s2 = self.model(x_s2, s2)
+        return cx * x - cm * phi_1 * m_s - (1.0 / r2) * cm * phi_2 * (m_s2 - m_s)
+
+    def multi_second(self, x, m_prev, t_prev, t):                    # :796-852
+        ns = self.ns
+        (m1, m0), (t1, t0) = m_prev[-2:], t_prev[-2:]
+        cx, cm, h = self._lin(t0, t)
+        r0 = (ns.lam(t0) - ns.lam(t1)) / h
+        D1_0 = (1.0 / r0) * (m0 - m1)
+        phi_1 = self._phi1(h)
+        return cx * x - cm * phi_1 * m0 - 0.5 * cm * phi_1 * D1_0
+
+    def multi_third(self, x, m_prev, t_prev, t):                     # :854-904
+        ns = self.ns
+        (m2, m1, m0), (t2, t1, t0) = m_prev[-3:], t_prev[-3:]
+        cx, cm, h = self._lin(t0, t)
+        r0, r1 = (ns.lam(t0) - ns.lam(t1)) / h, (ns.lam(t1) - ns.lam(t2)) / h
+        D1_0, D1_1 = (1.0 / r0) * (m0 - m1), (1.0 / r1) * (m1 - m2)
+        D1 = D1_0 + (r0 / (r0 + r1)) * (D1_0 - D1_1)
+        D2 = (1.0 / (r0 + r1)) * (D1_0 - D1_1)
+        if self.pp:
+            phi_1 = np.expm1(-h)
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            return cx * x - cm * phi_1 * m0 + cm * phi_2 * D1 - cm * phi_3 * D2
+        phi_1 = np.expm1(h)
+        phi_2 = phi_1 / h - 1.0
+        phi_3 = phi_2 / h - 0.5
+        return cx * x - cm * phi_1 * m0 - cm * phi_2 * D1 - cm * phi_3 * D2
+
+
+def dpm_solver_triple(K: int, algorithm: str = "dpmsolver++", method: str = "multistep", order: int = 3,
+                      skip_type: str = "time_quadratic", t_T: float = 1.0, t_0: float = 1e-3, lower_order_final: bool = False) -> CoeffTriple:
+    """`DPM_Solver.sample(steps=K, order, skip_type, method, lower_order_final, denoise_to_zero=False)` of
+    deps/dpm_solver_pytorch.py:1166-1232 as a K-row coefficient matrix (K = model calls).  multistep: order-1 start, then
+    order 2, then order 3 (:1171-1213); singlestep: the order schedule that uses up K calls (:514-538), r1/r2 from the inner
+    time grid (:1222-1227).  These are the samplers heading results/FID/dpmsolver*_*step.csv."""
+    if algorithm not in ("dpmsolver", "dpmsolver++"):
+        raise ValueError("algorithm must be 'dpmsolver' or 'dpmsolver++'")
+    ns = VPLinearSchedule()
+    tr = CoefficientTracer(K, ns)
+    U = _DpmUpdates(ns, algorithm == "dpmsolver++", tr)
+    x = tr.noise()
+    if method == "multistep":
+        if K < order:
+            raise ValueError("multistep needs steps >= order")
+        ts = solver_time_steps(skip_type, t_T, t_0, K, ns)
+        t_prev, m_prev = [ts[0]], [U.model(x, ts[0])]
+
+        def update(x, t, o):
+            if o == 1:
+                return U.first(x, t_prev[-1], t, m_prev[-1])
+            return U.multi_second(x, m_prev, t_prev, t) if o == 2 else U.multi_third(x, m_prev, t_prev, t)
+
+        for step in range(1, order):
+            x = update(x, ts[step], step)
+            t_prev.append(ts[step])
+            m_prev.append(U.model(x, ts[step]))
+        for step in range(order, K + 1):
+            o = min(order, K + 1 - step) if (lower_order_final and K < 10) else order
+            x = update(x, ts[step], o)
+            t_prev = t_prev[1:] + [ts[step]]
+            if step < K:
+                m_prev = m_prev[1:] + [U.model(x, ts[step])]
+        t_end = ts[-1]
+    elif method in ("singlestep", "singlestep_fixed"):
+        if method == "singlestep":
+            orders = singlestep_orders(K, order)
+            idx = np.cumsum([0] + orders)
+            outer = solver_time_steps(skip_type, t_T, t_0, K, ns)[idx] if skip_type != "logSNR" else solver_time_steps(skip_type, t_T, t_0, len(orders), ns)
+        else:
+            orders = [order] * (K // order)
+            if K % order:
+                raise ValueError("singlestep_fixed needs K divisible by order")
+            outer = solver_time_steps(skip_type, t_T, t_0, len(orders), ns)
+        for i, o in enumerate(orders):
+            s, t = outer[i], outer[i + 1]
+            inner = solver_time_steps(skip_type, s, t, o, ns)
+            lam = np.array([ns.lam(v) for v in inner])
+            h = lam[-1] - lam[0]
+            if o == 1:
+                x = U.first(x, s, t, U.model(x, s))
+            elif o == 2:
+                x = U.single_second(x, s, t, (lam[1] - lam[0]) / h)
+            else:
+                x = U.single_third(x, s, t, (lam[1] - lam[0]) / h, (lam[2] - lam[0]) / h)
+        t_end = outer[-1]
+    else:
+        raise ValueError("method must be 'multistep', 'singlestep' or 'singlestep_fixed'")
+    tag = {"dpmsolver": "dpmsolver", "dpmsolver++": "dpmsolverpp"}[algorithm]
+    return tr.finish(x, t_end, name=f"{tag}_{method}{order}_{K:03d}")
+
+
+# ----------------------------------------------------------------------------------------------
+# DEIS as the reference drives it for results/FID/deis_{5,10,15}step.csv (src/CIFAR10NaturalInference.py:166-178:
+# ts_phase "t" | "rho", ts_order 2, method t_ab | rho_ab | rho_rk, ab_order 2 | 3) plus iPNDM
+# ----------------------------------------------------------------------------------------------
+class _DeisVP:
+    """VP-linear quantities of deps/th_deis/vpsde.py:11-78 in float64: abar(t), psi, the eps integrand, rho(t) and t(rho)."""
+
+    def __init__(self, beta_0=0.1, beta_1=20.0):
+        self.b0, self.b1 = beta_0, beta_1
+
+    def log_abar(self, t):
+        return 2.0 * (-0.25 * t ** 2 * (self.b1 - self.b0) - 0.5 * t * self.b0)
+
+    def abar(self, t):
+        return np.exp(self.log_abar(t))
+
+    def t_of_abar(self, a):
+        c = np.log(a) / 2.0
+        qa, qb = 0.25 * (self.b1 - self.b0), 0.5 * self.b0
+        return (-qb + np.sqrt(qb * qb - 4.0 * qa * c)) / (2.0 * qa)
+
+    def psi(self, t0, t1):
+        return np.sqrt(self.abar(t1) / self.abar(t0))
+
+    def eps_integrand(self, t):
+        return -0.5 * (-t * (self.b1 - self.b0) - self.b0) / np.sqrt(1.0 - self.abar(t))
+
+    def rho(self, t):
+        a = self.abar(t)
+        return np.sqrt((1.0 - a) / a)
+
+    def t_of_rho(self, rho):
+        return self.t_of_abar(1.0 / (rho * rho + 1.0))
+
+    def rev_ts(self, num_step, ts_order=2, ts_phase="t", t1=1.0, t0=1e-3):
+        """deps/th_deis/sde.py:59-91 (continuous-time branch)"""
+        if ts_phase == "t":
+            return np.linspace(t1 ** (1.0 / ts_order), t0 ** (1.0 / ts_order), num_step + 1) ** ts_order
+        r0, r1 = self.rho(t0), self.rho(t1)
+        if ts_phase == "log":
+            return self.t_of_rho(np.exp(np.linspace(np.log(r1), np.log(r0), num_step + 1)))
+        if ts_phase == "rho":
+            p = 1.0 / ts_order
+            return self.t_of_rho((r1 ** p + np.arange(num_step + 1) / num_step * (r0 ** p - r1 ** p)) ** ts_order)
+        raise ValueError("ts_phase must be 't', 'log' or 'rho'")
+
+
+def _ab_coefficients(grid, psi, integrand, ab_order: int, quad_points: int = 10000):
+    """`get_ab_eps_coef` (deps/th_deis/multistep.py:6-96): C[i, j] multiplies eps_{i-j}; step i uses order min(i, ab_order);
+    C_ij = left Riemann sum over [g_i, g_{i+1}) of psi(tau, g_{i+1}) * integrand(tau) * Lagrange_j(tau)."""
+    n = len(grid) - 1
+    C = np.zeros((n, ab_order + 1))
+    for i in range(n):
+        s, t = grid[i], grid[i + 1]
+        o = min(i, ab_order)
+        tau = np.linspace(s, t, quad_points, endpoint=False)
+        dt = (t - s) / quad_points
+        w = psi(tau, t) * integrand(tau)
+        nodes = grid[i - o: i + 1]
+        for j in range(o + 1):
+            k = o - j  # node of eps_{i-j}
+            num = tau[:, None] - nodes[None, :]
+            den = nodes[k] - nodes
+            num[:, k], den[k] = 1.0, 1.0
+            C[i, j] = float(np.sum(w * np.prod(num, axis=1) / np.prod(den)) * dt)
+    return C
+
+
+RK_TABLEAUS = {  # deps/th_deis/rk.py: (c, a rows, b)
+    "1euler": ([0.0], [[]], [1.0]),
+    "2heun": ([0.0, 1.0], [[], [1.0]], [0.5, 0.5]),
+    "3kutta": ([0.0, 0.5, 1.0], [[], [0.5], [-1.0, 2.0]], [1 / 6, 4 / 6, 1 / 6]),
+    "3ral": ([0.0, 0.5, 0.75], [[], [0.5], [0.0, 0.75]], [2 / 9, 1 / 3, 4 / 9]),
+    "3heun": ([0.0, 1 / 3, 2 / 3], [[], [1 / 3], [0.0, 2 / 3]], [0.25, 0.0, 0.75]),
+    "3vdh": ([0.0, 8 / 15, 2 / 3], [[], [8 / 15], [0.25, 5 / 12]], [0.25, 0.0, 0.75]),
+    "3ssprk": ([0.0, 1.0, 0.5], [[], [1.0], [0.25, 0.25]], [1 / 6, 1 / 6, 2 / 3]),
+    "4rk": ([0.0, 0.5, 0.5, 1.0], [[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0]], [1 / 6, 2 / 6, 2 / 6, 1 / 6]),
+}
+
+
+def deis_triple(num_step: int, method: str = "rho_rk", ab_order: int = 3, rk_method: str = "3kutta", ts_phase: str = "t",
+                ts_order: int = 2, t_T: float = 1.0, t_0: float = 1e-3, quad_points: int = 10000) -> CoeffTriple:
+    """`th_deis.get_sampler(sde, eps_fn, ts_phase, ts_order, num_step, method, ab_order, rk_method)` (deps/th_deis/sampler.py:15-160)
+    on the VP-linear SDE as a coefficient matrix:
+      t_ab    exponential integrator, Adams-Bashforth in t (:26-49)                              K = num_step rows
+      rho_ab  Adams-Bashforth in rho on v = x / sqrt(abar): dv/drho = eps (:98-133)               K = num_step rows
+      rho_rk  Runge-Kutta in rho (default Kutta's third order, rk.py:17-25) (:136-160)            K = stages * num_step rows
+      ipndm   DDIM step with the linear-multistep combination of the last 4 eps, uniform t grid (:50-95)
+    The model is always called on x = v * sqrt(abar(t)) at t = t(rho), as `eps_fn_vrho` does."""
+    vp = _DeisVP()
+    ns = VPLinearSchedule(vp.b0, vp.b1)
+    if method == "t_ab":
+        return deis_tab_triple(num_step, ab_order, t_T, t_0, quad_points) if (ts_phase == "t" and ts_order == 2) else _deis_tab_on(vp.rev_ts(num_step, ts_order, ts_phase, t_T, t_0), ab_order, quad_points)
+    if method == "ipndm":
+        ts = vp.rev_ts(num_step, 1, "t", t_T, t_0)
+        tr = CoefficientTracer(num_step, ns)
+        x, hist = tr.noise(), []
+        lin = [[1.0], [1.5, -0.5], [23 / 12, -16 / 12, 5 / 12], [55 / 24, -59 / 24, 37 / 24, -9 / 24]]
+        for i in range(num_step):
+            s, t = ts[i], ts[i + 1]
+            hist.insert(0, tr.model_eps(x, s))
+            ddim = np.sqrt(1 - vp.abar(t)) - np.sqrt(vp.abar(t) / vp.abar(s)) * np.sqrt(1 - vp.abar(s))
+            x = vp.psi(s, t) * x + ddim * sum(c * e for c, e in zip(lin[min(i, 3)], hist))
+            hist = hist[:4]
+        return tr.finish(x, ts[-1], name=f"deis_ipndm_{num_step:03d}")
+    ts = vp.rev_ts(num_step, ts_order, ts_phase, t_T, t_0)
+    rhos = vp.rho(ts)
+    to_x = lambda v, t: v * np.sqrt(vp.abar(t))
+    if method == "rho_ab":
+        C = _ab_coefficients(rhos, lambda a, b: np.ones_like(a), lambda a: np.ones_like(a), ab_order, quad_points)
+        tr = CoefficientTracer(num_step, ns)
+        v, hist = tr.noise() / np.sqrt(vp.abar(ts[0])), []
+        for i in range(num_step):
+            t_i = vp.t_of_rho(rhos[i])
+            hist.insert(0, tr.model_eps(to_x(v, t_i), t_i))
+            v = v + sum(C[i, j] * hist[j] for j in range(min(i, ab_order) + 1))
+            hist = hist[:ab_order]
+        return tr.finish(to_x(v, ts[-1]), ts[-1], name=f"deis_rho_ab{ab_order}_{num_step:03d}")
+    if method == "rho_rk":
+        c, a, b = RK_TABLEAUS[rk_method]
+        tr = CoefficientTracer(len(c) * num_step, ns)
+        v = tr.noise() / np.sqrt(vp.abar(ts[0]))
+        for i in range(num_step):
+            d = rhos[i + 1] - rhos[i]
+            ks = []
+            for st in range(len(c)):
+                vv = v + d * sum(a[st][q] * ks[q] for q in range(st)) if st else v
+                t_st = vp.t_of_rho(rhos[i] + d * c[st])
+                ks.append(tr.model_eps(to_x(vv, t_st), t_st))
+            v = v + d * sum(bq * kq for bq, kq in zip(b, ks))
+        return tr.finish(to_x(v, ts[-1]), ts[-1], name=f"deis_rho_rk_{rk_method}_{len(c) * num_step:03d}")
+    raise ValueError("method must be t_ab, rho_ab, rho_rk or ipndm")
+
+
+def _deis_tab_on(ts, ab_order, quad_points):
+    """t_ab on an arbitrary reverse time grid (deis_tab_triple is the quadratic-grid special case)"""
+    vp = _DeisVP()
+    ns = VPLinearSchedule(vp.b0, vp.b1)
+    K = len(ts) - 1
+    C = _ab_coefficients(ts, vp.psi, vp.eps_integrand, ab_order, quad_points)
+    tr = CoefficientTracer(K, ns)
+    x, hist = tr.noise(), []
+    for i in range(K):
+        hist.insert(0, tr.model_eps(x, ts[i]))
+        x = vp.psi(ts[i], ts[i + 1]) * x + sum(C[i, j] * hist[j] for j in range(min(i, ab_order) + 1))
+        hist = hist[:ab_order]
+    return tr.finish(x, ts[-1], name=f"deis_tab_{K:03d}")
 
 
 # ----------------------------------------------------------------------------------------------

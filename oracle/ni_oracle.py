@@ -498,3 +498,289 @@ def deis_tab_original_loop(ts, eps_model, noise, ab_order=3):
             nxt = nxt + c * e
         x, eps_pred = nxt, full[:-1]
     return x
+
+
+# --------------------------------------------------------------------------------------
+# DPM-Solver / DPM-Solver++ `sample()` in general: multistep | singlestep, order 1..3 (comparators for the generated
+# matrices of the samplers heading results/FID/dpmsolver*_*.csv).  Restated from deps/dpm_solver_pytorch.py with the
+# reference's own control flow (model_prev_list / t_prev_list; inner time grids for r1, r2); pinned in
+# tests/test_oracle_golden.py by running THIS code in coefficient space against matrices produced by the reference's
+# unmodified DPM_Solver class (tests/golden/solver_matrices.npz).
+# --------------------------------------------------------------------------------------
+class _VPSchedule:
+    """NoiseScheduleVP('linear') (deps/dpm_solver_pytorch.py:128-167) on scalars of `dtype`."""
+
+    def __init__(self, dtype=torch.float32, b0=0.1, b1=20.0):
+        self.dt, self.b0, self.b1 = dtype, b0, b1
+
+    def T(self, v):
+        return torch.as_tensor(v, dtype=self.dt)
+
+    def log_alpha(self, t):
+        t = self.T(t)
+        return -0.25 * t**2 * (self.b1 - self.b0) - 0.5 * t * self.b0
+
+    def alpha(self, t):
+        return torch.exp(self.log_alpha(t))
+
+    def std(self, t):
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.log_alpha(t)))
+
+    def lam(self, t):
+        la = self.log_alpha(t)
+        return la - 0.5 * torch.log(1.0 - torch.exp(2.0 * la))
+
+    def inverse_lambda(self, lamb):
+        lamb = self.T(lamb)
+        tmp = 2.0 * (self.b1 - self.b0) * torch.logaddexp(-2.0 * lamb, torch.zeros((1,), dtype=self.dt))[0]
+        delta = self.b0**2 + tmp
+        return tmp / (torch.sqrt(delta) + self.b0) / (self.b1 - self.b0)
+
+    def time_steps(self, skip_type, t_T, t_0, N):
+        """get_time_steps (:455-482)"""
+        if skip_type == "time_uniform":
+            return torch.linspace(float(t_T), float(t_0), N + 1, dtype=self.dt)
+        if skip_type == "time_quadratic":
+            return torch.linspace(float(t_T) ** 0.5, float(t_0) ** 0.5, N + 1, dtype=self.dt) ** 2
+        if skip_type == "logSNR":
+            return torch.stack([self.inverse_lambda(v) for v in torch.linspace(float(self.lam(t_T)), float(self.lam(t_0)), N + 1, dtype=self.dt)])
+        raise ValueError(skip_type)
+
+
+@torch.no_grad()
+def dpm_solver_original_sample(eps_model, noise, steps, algorithm="dpmsolver++", method="multistep", order=3, skip_type="time_quadratic",
+                               t_T=1.0, t_0=1e-3, lower_order_final=False, dtype=torch.float32):
+    """`DPM_Solver(eps_model, NoiseScheduleVP('linear'), algorithm_type).sample(noise, steps, t_T, t_0, order, skip_type, method,
+    lower_order_final, denoise_to_zero=False)` (:1166-1232), solver_type 'dpmsolver', no thresholding."""
+    ns = _VPSchedule(dtype)
+    pp = algorithm == "dpmsolver++"
+
+    def model_fn(x, t):  # :262-271 data_prediction_fn / noise_prediction_fn
+        e = eps_model(x, float(t))
+        return (x - ns.std(t) * e) / ns.alpha(t) if pp else e
+
+    def first(x, s, t, model_s):  # :547-592
+        h = ns.lam(t) - ns.lam(s)
+        if pp:
+            return ns.std(t) / ns.std(s) * x - ns.alpha(t) * torch.expm1(-h) * model_s
+        return torch.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - (ns.std(t) * torch.expm1(h)) * model_s
+
+    def single2(x, s, t, r1):  # :594-676
+        h = ns.lam(t) - ns.lam(s)
+        s1 = ns.inverse_lambda(ns.lam(s) + r1 * h)
+        model_s = model_fn(x, s)
+        if pp:
+            phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
+            x_s1 = (ns.std(s1) / ns.std(s)) * x - (ns.alpha(s1) * phi_11) * model_s
+            model_s1 = model_fn(x_s1, s1)
+            return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * model_s - (0.5 / r1) * (ns.alpha(t) * phi_1) * (model_s1 - model_s)
+        phi_11, phi_1 = torch.expm1(r1 * h), torch.expm1(h)
+        x_s1 = torch.exp(ns.log_alpha(s1) - ns.log_alpha(s)) * x - (ns.std(s1) * phi_11) * model_s
+        model_s1 = model_fn(x_s1, s1)
+        return torch.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - (ns.std(t) * phi_1) * model_s - (0.5 / r1) * (ns.std(t) * phi_1) * (model_s1 - model_s)
+
+    def single3(x, s, t, r1, r2):  # :677-795
+        h = ns.lam(t) - ns.lam(s)
+        s1, s2 = ns.inverse_lambda(ns.lam(s) + r1 * h), ns.inverse_lambda(ns.lam(s) + r2 * h)
+        model_s = model_fn(x, s)
+        if pp:
+            phi_11, phi_12, phi_1 = torch.expm1(-r1 * h), torch.expm1(-r2 * h), torch.expm1(-h)
+            phi_22, phi_2 = phi_12 / (r2 * h) + 1.0, phi_1 / h + 1.0
+            x_s1 = (ns.std(s1) / ns.std(s)) * x - (ns.alpha(s1) * phi_11) * model_s
+            model_s1 = model_fn(x_s1, s1)
+            x_s2 = (ns.std(s2) / ns.std(s)) * x - (ns.alpha(s2) * phi_12) * model_s + r2 / r1 * (ns.alpha(s2) * phi_22) * (model_s1 - model_s)
+            model_s2 = model_fn(x_s2, s2)
+            return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * model_s + (1.0 / r2) * (ns.alpha(t) * phi_2) * (model_s2 - model_s)
+        phi_11, phi_12, phi_1 = torch.expm1(r1 * h), torch.expm1(r2 * h), torch.expm1(h)
+        phi_22, phi_2 = phi_12 / (r2 * h) - 1.0, phi_1 / h - 1.0
+        x_s1 = torch.exp(ns.log_alpha(s1) - ns.log_alpha(s)) * x - (ns.std(s1) * phi_11) * model_s
+        model_s1 = model_fn(x_s1, s1)
+        x_s2 = torch.exp(ns.log_alpha(s2) - ns.log_alpha(s)) * x - (ns.std(s2) * phi_12) * model_s - r2 / r1 * (ns.std(s2) * phi_22) * (model_s1 - model_s)
+        model_s2 = model_fn(x_s2, s2)
+        return torch.exp(ns.log_alpha(t) - ns.log_alpha(s)) * x - (ns.std(t) * phi_1) * model_s - (1.0 / r2) * (ns.std(t) * phi_2) * (model_s2 - model_s)
+
+    def multi2(x, model_prev_list, t_prev_list, t):  # :796-852
+        model_prev_1, model_prev_0 = model_prev_list[-2], model_prev_list[-1]
+        t_prev_1, t_prev_0 = t_prev_list[-2], t_prev_list[-1]
+        h_0, h = ns.lam(t_prev_0) - ns.lam(t_prev_1), ns.lam(t) - ns.lam(t_prev_0)
+        D1_0 = (1.0 / (h_0 / h)) * (model_prev_0 - model_prev_1)
+        if pp:
+            phi_1 = torch.expm1(-h)
+            return (ns.std(t) / ns.std(t_prev_0)) * x - (ns.alpha(t) * phi_1) * model_prev_0 - 0.5 * (ns.alpha(t) * phi_1) * D1_0
+        phi_1 = torch.expm1(h)
+        return torch.exp(ns.log_alpha(t) - ns.log_alpha(t_prev_0)) * x - (ns.std(t) * phi_1) * model_prev_0 - 0.5 * (ns.std(t) * phi_1) * D1_0
+
+    def multi3(x, model_prev_list, t_prev_list, t):  # :854-904
+        model_prev_2, model_prev_1, model_prev_0 = model_prev_list
+        t_prev_2, t_prev_1, t_prev_0 = t_prev_list
+        h_1, h_0, h = ns.lam(t_prev_1) - ns.lam(t_prev_2), ns.lam(t_prev_0) - ns.lam(t_prev_1), ns.lam(t) - ns.lam(t_prev_0)
+        r0, r1 = h_0 / h, h_1 / h
+        D1_0 = (1.0 / r0) * (model_prev_0 - model_prev_1)
+        D1_1 = (1.0 / r1) * (model_prev_1 - model_prev_2)
+        D1 = D1_0 + (r0 / (r0 + r1)) * (D1_0 - D1_1)
+        D2 = (1.0 / (r0 + r1)) * (D1_0 - D1_1)
+        if pp:
+            phi_1 = torch.expm1(-h)
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            return (ns.std(t) / ns.std(t_prev_0)) * x - (ns.alpha(t) * phi_1) * model_prev_0 + (ns.alpha(t) * phi_2) * D1 - (ns.alpha(t) * phi_3) * D2
+        phi_1 = torch.expm1(h)
+        phi_2 = phi_1 / h - 1.0
+        phi_3 = phi_2 / h - 0.5
+        return (torch.exp(ns.log_alpha(t) - ns.log_alpha(t_prev_0)) * x - (ns.std(t) * phi_1) * model_prev_0 - (ns.std(t) * phi_2) * D1
+                - (ns.std(t) * phi_3) * D2)
+
+    def multistep_update(x, model_prev_list, t_prev_list, t, o):  # :932-954
+        if o == 1:
+            return first(x, t_prev_list[-1], t, model_prev_list[-1])
+        return multi2(x, model_prev_list, t_prev_list, t) if o == 2 else multi3(x, model_prev_list, t_prev_list, t)
+
+    x = noise.clone()
+    if method == "multistep":  # :1171-1213
+        timesteps = ns.time_steps(skip_type, t_T, t_0, steps)
+        t = timesteps[0]
+        t_prev_list, model_prev_list = [t], [model_fn(x, t)]
+        for step in range(1, order):
+            t = timesteps[step]
+            x = multistep_update(x, model_prev_list, t_prev_list, t, step)
+            t_prev_list.append(t)
+            model_prev_list.append(model_fn(x, t))
+        for step in range(order, steps + 1):
+            t = timesteps[step]
+            step_order = min(order, steps + 1 - step) if (lower_order_final and steps < 10) else order
+            x = multistep_update(x, model_prev_list, t_prev_list, t, step_order)
+            for i in range(order - 1):
+                t_prev_list[i], model_prev_list[i] = t_prev_list[i + 1], model_prev_list[i + 1]
+            t_prev_list[-1] = t
+            if step < steps:
+                model_prev_list[-1] = model_fn(x, t)
+        return x
+    # singlestep (:1214-1232 with the order schedule of :514-538)
+    if order == 3:
+        Kk = steps // 3 + 1
+        orders = [3] * (Kk - 2) + [2, 1] if steps % 3 == 0 else ([3] * (Kk - 1) + [1] if steps % 3 == 1 else [3] * (Kk - 1) + [2])
+    elif order == 2:
+        orders = [2] * (steps // 2) if steps % 2 == 0 else [2] * (steps // 2) + [1]
+    else:
+        orders = [1] * steps
+    cum = [0]
+    for o in orders:
+        cum.append(cum[-1] + o)
+    timesteps_outer = ns.time_steps(skip_type, t_T, t_0, steps)[torch.tensor(cum)]
+    for step, o in enumerate(orders):
+        s, t = timesteps_outer[step], timesteps_outer[step + 1]
+        inner = ns.time_steps(skip_type, float(s), float(t), o)
+        lambda_inner = torch.stack([ns.lam(v) for v in inner])
+        h = lambda_inner[-1] - lambda_inner[0]
+        if o == 1:
+            x = first(x, s, t, model_fn(x, s))
+        elif o == 2:
+            x = single2(x, s, t, (lambda_inner[1] - lambda_inner[0]) / h)
+        else:
+            x = single3(x, s, t, (lambda_inner[1] - lambda_inner[0]) / h, (lambda_inner[2] - lambda_inner[0]) / h)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# DEIS rho-AB, rho-RK and iPNDM (deps/th_deis/sampler.py:50-160, rk.py, multistep.py): original loops on tensors.
+# th_deis is jax code (absent here): restated; no reference output exists to pin these three beyond (i) the shared
+# Adams-Bashforth coefficient routine, which reproduces the shipped results/deis/deis_tab_* matrices, and (ii) the classical
+# AB / RK / linear-multistep tables they reduce to -- "parity unpinned" for rho_ab / rho_rk / ipndm.
+# --------------------------------------------------------------------------------------
+def _deis_abar(t, b0=0.1, b1=20.0):
+    t = np.asarray(t, dtype=np.float64)
+    return np.exp(2.0 * (-0.25 * t**2 * (b1 - b0) - 0.5 * t * b0))
+
+
+def _deis_t_of_abar(a, b0=0.1, b1=20.0):
+    c = np.log(np.asarray(a, dtype=np.float64)) / 2.0
+    qa, qb = 0.25 * (b1 - b0), 0.5 * b0
+    return (-qb + np.sqrt(qb**2 - 4 * qa * c)) / 2 / qa          # vpsde.py:8-10 quad_root
+
+
+def deis_rev_ts(num_step, ts_order=2, ts_phase="t", t1=1.0, t0=1e-3):
+    """get_rev_ts (deps/th_deis/sde.py:59-91), continuous-time SDE"""
+    rho = lambda t: np.sqrt((1 - _deis_abar(t)) / _deis_abar(t))        # vpsde.py:65-67 with alpha_start = 1
+    t_of_rho = lambda r: _deis_t_of_abar(1.0 / (r**2 + 1.0))           # :69-73
+    if ts_phase == "t":
+        return np.power(np.linspace(t1 ** (1.0 / ts_order), t0 ** (1.0 / ts_order), num_step + 1), ts_order)
+    r0, r1 = rho(t0), rho(t1)
+    if ts_phase == "log":
+        return t_of_rho(np.exp(np.linspace(np.log(r1), np.log(r0), num_step + 1)))
+    return t_of_rho(np.power(r1 ** (1.0 / ts_order) + np.linspace(0, num_step, num_step + 1) / num_step * (r0 ** (1.0 / ts_order) - r1 ** (1.0 / ts_order)), ts_order))
+
+
+def deis_rho_ab_coefficients(rhos, ab_order=3, num_item=10000):
+    """get_ab_eps_coef with the HelperSDE of sampler.py:104-109 (psi = 1, integrand = 1): plain Adams-Bashforth weights on the
+    rho grid, by the same 10000-point left Riemann sums; coef[i, j] multiplies eps_{i-j}."""
+    rhos = np.asarray(rhos, dtype=np.float64)
+    coef = np.zeros((len(rhos) - 1, ab_order + 1))
+    for i in range(len(rhos) - 1):
+        order = min(i, ab_order)
+        inter = np.linspace(rhos[i], rhos[i + 1], num_item, endpoint=False)
+        d = (rhos[i + 1] - rhos[i]) / num_item
+        poly_ts = rhos[i - order: i + 1]
+        for out_j, coef_idx in enumerate(range(order, -1, -1)):
+            poly = np.ones_like(inter)
+            for k in range(order + 1):
+                if k != coef_idx:
+                    poly *= (inter - poly_ts[k]) / (poly_ts[coef_idx] - poly_ts[k])
+            coef[i, out_j] = np.sum(poly) * d
+    return coef
+
+
+@torch.no_grad()
+def deis_original_sample(eps_model, noise, num_step, method="rho_rk", ab_order=3, rk_method="3kutta", ts_phase="t", ts_order=2):
+    """th_deis.get_sampler(...)(noise) for method rho_ab | rho_rk | ipndm (t_ab: deis_tab_original_loop above)."""
+    f32 = lambda v: torch.tensor(float(v), dtype=torch.float32, device=noise.device)
+    if method == "ipndm":  # sampler.py:50-95
+        ts = deis_rev_ts(num_step, 1, "t")
+        lin = [[1.0, 0, 0, 0], [1.5, -0.5, 0, 0], [23 / 12.0, -16 / 12.0, 5 / 12.0, 0], [55 / 24.0, -59 / 24.0, 37 / 24.0, -9 / 24.0]]
+        x, eps_pred = noise.clone(), [noise] * 3
+        for i in range(num_step):
+            a_cur, a_next = _deis_abar(ts[i]), _deis_abar(ts[i + 1])
+            ddim = np.sqrt(1 - a_next) - np.sqrt(a_next / a_cur) * np.sqrt(1 - a_cur)
+            full = [eps_model(x, float(ts[i])), *eps_pred]
+            nxt = f32(np.sqrt(a_next / a_cur)) * x
+            for c, e in zip(lin[min(i, 3)], full):
+                nxt = nxt + f32(ddim * c) * e
+            x, eps_pred = nxt, full[:-1]
+        return x
+    ts = deis_rev_ts(num_step, ts_order, ts_phase)
+    abar = _deis_abar(ts)
+    rhos = np.sqrt((1 - abar) / abar)
+    t_of_rho = lambda r: float(_deis_t_of_abar(1.0 / (r**2 + 1.0)))
+    v2x = lambda v, t: v / f32(np.sqrt(1.0 / _deis_abar(t)))      # vpsde.py:75-81
+    v = f32(np.sqrt(1.0 / abar[0])) * noise
+    if method == "rho_ab":  # sampler.py:98-133
+        coef = deis_rho_ab_coefficients(rhos, ab_order)
+        eps_pred = [noise] * ab_order
+        for i in range(num_step):
+            t_cur = t_of_rho(rhos[i])
+            full = [eps_model(v2x(v, t_cur), t_cur), *eps_pred]
+            nxt = v.clone()
+            for c, e in zip(coef[i], full):
+                nxt = nxt + f32(c) * e
+            v, eps_pred = nxt, full[:-1]
+        return v2x(v, ts[-1])
+    if method == "rho_rk":  # sampler.py:136-160 + rk.py
+        tabs = {"1euler": ([0.0], [[]], [1.0]), "2heun": ([0.0, 1.0], [[], [1.0]], [0.5, 0.5]),
+                "3kutta": ([0.0, 0.5, 1.0], [[], [0.5], [-1.0, 2.0]], [1.0 / 6, 4.0 / 6, 1.0 / 6]),
+                "3heun": ([0.0, 1.0 / 3, 2.0 / 3], [[], [1.0 / 3], [0.0, 2.0 / 3]], [0.25, 0.0, 0.75]),
+                "4rk": ([0.0, 0.5, 0.5, 1.0], [[], [0.5], [0.0, 0.5], [0.0, 0.0, 1.0]], [1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6])}
+        c, a, b = tabs[rk_method]
+        fn = lambda vv, rho: eps_model(v2x(vv, t_of_rho(rho)), t_of_rho(rho))
+        for i in range(num_step):
+            dt = rhos[i + 1] - rhos[i]
+            ks = []
+            for st in range(len(c)):
+                vv = v
+                for q in range(st):
+                    if a[st][q] != 0.0:
+                        vv = vv + f32(dt * a[st][q]) * ks[q]
+                ks.append(fn(vv, rhos[i] + dt * c[st]))
+            for bq, kq in zip(b, ks):
+                if bq != 0.0:
+                    v = v + f32(dt * bq) * kq
+        return v2x(v, ts[-1])
+    raise ValueError(method)

@@ -130,3 +130,9 @@ def score_sde_vp():
         sys.modules.pop("sde_lib", None)
         return sde_lib.VPSDE, mutils.get_score_fn
     return _with_stubs(["ml_collections", "op"], go)
+
+
+def dpm_solver_module():
+    """deps/dpm_solver_pytorch.py (pure torch): NoiseScheduleVP, DPM_Solver -- the original samplers behind
+    results/FID/dpmsolver*_*.csv."""
+    return _load(os.path.join(REF_ROOT, "deps", "dpm_solver_pytorch.py"), "_ref_dpm_solver")

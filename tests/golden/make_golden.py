@@ -214,7 +214,55 @@ def gen_matrices():
     np.savez_compressed(os.path.join(HERE, "reference_matrices.npz"), **out)
 
 
+def gen_solver_matrices():
+    """Coefficient matrices of the ORIGINAL DPM-Solver / DPM-Solver++ samplers, obtained by running the reference's own
+    `DPM_Solver.sample` (deps/dpm_solver_pytorch.py, unmodified) in coefficient space: x lives in R^(2K+1) over the basis
+    (y_0..y_{K-1}, eps_0..eps_K), the j-th model call returns (x - alpha y_j)/sigma and records x as row j-1 of [A|B]
+    (what src/AnalyzeDPMSolver.py does with sympy).  Same arguments as the FID runs of
+    src/CIFAR10NaturalInference.py:363-393 (time_quadratic, lower_order_final=False, denoise_to_zero=False), in float64
+    (the reference's float32 time grid is a precision detail, not part of the sampler)."""
+    dpm = ref_loader.dpm_solver_module()
+    torch.set_default_dtype(torch.float64)
+    out = {}
+    try:
+        for K in (5, 10, 15):
+            for alg in ("dpmsolver", "dpmsolver++"):
+                for method, order in (("multistep", 2), ("multistep", 3), ("singlestep", 2), ("singlestep", 3)):
+                    ns = dpm.NoiseScheduleVP("linear", continuous_beta_0=0.1, continuous_beta_1=20.0)
+                    rows, nodes = [], []
+
+                    def noise_fn(x, t):
+                        tt = t.reshape(-1)[:1]
+                        if nodes:
+                            rows.append(x[0].clone())
+                        j = len(nodes)
+                        nodes.append([float(tt), float(ns.marginal_alpha(tt)), float(ns.marginal_std(tt))])
+                        y = torch.zeros_like(x)
+                        y[0, j] = 1.0
+                        return (x - ns.marginal_alpha(tt) * y) / ns.marginal_std(tt)
+
+                    solver = dpm.DPM_Solver(noise_fn, ns, algorithm_type=alg)
+                    x0 = torch.zeros(1, 2 * K + 1)
+                    x0[0, K] = 1.0
+                    xe = solver.sample(x0, steps=K, t_start=1.0, t_end=1e-3, order=order, skip_type="time_quadratic", method=method,
+                                       denoise_to_zero=False, lower_order_final=False)
+                    rows.append(xe[0].clone())
+                    t_end = torch.tensor([1e-3])
+                    nodes.append([1e-3, float(ns.marginal_alpha(t_end)), float(ns.marginal_std(t_end))])
+                    assert len(rows) == K and len(nodes) == K + 1, (K, alg, method, order, len(rows), len(nodes))
+                    M = torch.stack(rows).numpy()
+                    key = f"{alg}/{method}{order}/{K:03d}"
+                    out[key + "/A"], out[key + "/B"], out[key + "/node"] = M[:, :K], M[:, K:], np.array(nodes)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(HERE, "solver_matrices.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "solvers":
+        gen_solver_matrices()
+        raise SystemExit(0)
+    gen_solver_matrices()
     gen_weights()
     gen_cifar()
     gen_validate()

@@ -11,7 +11,7 @@ import pytest
 import naturaldiffusion_b200 as ni
 from naturaldiffusion_b200 import _lib, generators
 from naturaldiffusion_b200.coeffs import (CoeffTriple, build_plan, ddim_x0_coeffs, flow_match_sigmas, io_score_vp,
-                                           load_weight_csv, spaced_timesteps)
+                                           load_weight_csv, markov_ratios, spaced_timesteps)
 from naturaldiffusion_b200.sampler import shard_range
 from oracle import ni_oracle as O
 
@@ -285,7 +285,7 @@ def test_generators_match_reference_matrices(golden_dir):
             key = f"{fam}/{fam}_{K:03d}"
             assert np.abs(t.A - m[key + "/A"]).max() < 1e-14 and np.abs(t.B - m[key + "/B"]).max() < 1e-14
             assert np.array_equal(t.node, m[key + "/node"])
-            assert generators.markov_ratio(t) is not None
+            assert markov_ratios(t) is not None
     for K in (18, 24):
         t = generators.flow_euler_triple(K)
         key = f"flow_euler/flow_euler_simpy_{K:03d}"
@@ -296,7 +296,7 @@ def test_generators_match_reference_matrices(golden_dir):
             t, (A, B, node) = fn(K), ofn(K)
             assert np.abs(t.A - A).max() < 1e-14 and np.abs(t.B - B).max() < 1e-14 and np.array_equal(t.node, node)
     m42 = CoeffTriple(*[m["dpmsolverpp/dpmsolverpp2s_024/" + n] for n in ("A", "B", "node")])
-    assert generators.markov_ratio(m42) is None  # higher-order solvers are not Markov in the rows
+    assert markov_ratios(m42) is None  # higher-order solvers are not Markov in the rows
 
 
 def test_markov_structure_detection_and_identity(weights_dir):

@@ -1,0 +1,128 @@
+"""CPU: the original samplers that head the reference's FID tables (results/FID/{dpmsolver,dpmsolverpp,deis}_*step.csv) as
+coefficient matrices.  The generators (product, coefficient space) and the oracle's tensor-level
+restatements of the ORIGINAL loops are written independently; both are pinned here:
+  * DPM-Solver / DPM-Solver++ multistep-2/3 and singlestep-2/3 on the 5/10/15-step quadratic grids against matrices that
+    tests/golden/make_golden.py obtained from the reference's unmodified DPM_Solver class (solver_matrices.npz);
+  * DEIS rho-AB / rho-RK / iPNDM (th_deis is jax: nothing to run here) against each other and against the classical
+    Adams-Bashforth / Runge-Kutta tables they reduce to."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from naturaldiffusion_b200 import generators as G
+from oracle import ni_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_matrices.npz")
+SETTINGS = [(K, alg, method, order) for K in (5, 10, 15) for alg in ("dpmsolver", "dpmsolver++")
+            for method, order in (("multistep", 2), ("multistep", 3), ("singlestep", 2), ("singlestep", 3))]
+
+
+def test_dpm_solver_generators_match_the_reference_solver_class():
+    z = np.load(GOLD)
+    for K, alg, method, order in SETTINGS:
+        t = G.dpm_solver_triple(K, alg, method, order)
+        key = f"{alg}/{method}{order}/{K:03d}"
+        scale = max(1.0, np.abs(z[key + "/A"]).max())
+        assert np.abs(t.A - z[key + "/A"]).max() < 1e-11 * scale, key
+        assert np.abs(t.B - z[key + "/B"]).max() < 1e-11 * scale, key
+        assert np.abs(t.node - z[key + "/node"]).max() < 1e-12, key
+        assert np.all(t.B[:, 1:] == 0)  # deterministic samplers: only the initial noise
+
+
+def test_oracle_dpm_solver_restatement_matches_the_reference_solver_class():
+    """the oracle's tensor-level sample() run in coefficient space (fp64) reproduces the same goldens"""
+    z = np.load(GOLD)
+    for K, alg, method, order in SETTINGS:
+        ns = O._VPSchedule(torch.float64)
+        rows, calls = [], [0]
+
+        def eps_model(x, t):
+            if calls[0] > 0:
+                rows.append(x[0].clone())
+            y = torch.zeros_like(x)
+            y[0, calls[0]] = 1.0
+            calls[0] += 1
+            return (x - ns.alpha(t) * y) / ns.std(t)
+
+        x0 = torch.zeros(1, 2 * K + 1, dtype=torch.float64)
+        x0[0, K] = 1.0
+        xe = O.dpm_solver_original_sample(eps_model, x0, K, alg, method, order, dtype=torch.float64)
+        rows.append(xe[0])
+        M = torch.stack(rows).numpy()
+        key = f"{alg}/{method}{order}/{K:03d}"
+        scale = max(1.0, np.abs(z[key + "/A"]).max())
+        assert calls[0] == K and np.abs(M[:, :K] - z[key + "/A"]).max() < 1e-11 * scale and np.abs(M[:, K:] - z[key + "/B"]).max() < 1e-11 * scale, key
+
+
+def _apply_matrix(t, eps_model, noise):
+    """x_{k+1} = sum_j A[k,j] x0_j + B[k,0] eps_0 with x0_k = (x_k - sigma_k eps)/alpha_k, plain torch fp64"""
+    ts, al, sg = t.node[:, 0], t.node[:, 1], t.node[:, 2]
+    x, x0s = noise.clone(), []
+    for k in range(t.K):
+        x0s.append((x - sg[k] * eps_model(x, float(ts[k]))) / al[k])
+        x = sum(t.A[k, j] * x0s[j] for j in range(k + 1)) + t.B[k, 0] * noise
+    return x
+
+
+@pytest.mark.parametrize("method,kw", [("rho_ab", dict(ab_order=3)), ("rho_ab", dict(ab_order=2)), ("rho_rk", dict()),
+                                       ("rho_rk", dict(rk_method="2heun")), ("ipndm", dict()), ("rho_ab", dict(ts_phase="rho")),
+                                       ("rho_rk", dict(ts_phase="rho"))])
+def test_deis_matrices_equal_the_original_loops(method, kw):
+    torch.manual_seed(0)
+    noise = torch.randn(4, 3, 8, 8, dtype=torch.float64)
+    sgm = lambda t: float(np.sqrt(1 - O._deis_abar(t)))
+    eps_model = lambda x, t: sgm(t) * x + 0.1 * torch.tanh(1.3 * x + t)
+    for n in (5, 10, 15):
+        t = G.deis_triple(n, method, **kw)
+        a = _apply_matrix(t, eps_model, noise)
+        b = O.deis_original_sample(eps_model, noise, n, method, **kw)
+        assert float((a - b).abs().max() / b.norm()) < 2e-6, (method, kw, n)
+
+
+def test_deis_building_blocks_reduce_to_the_classical_tables():
+    # Adams-Bashforth weights on a uniform grid: h * (23, -16, 5)/12 and h * (3, -1)/2 (Riemann-sum accuracy 1/10000)
+    grid = np.linspace(3.0, 1.0, 9)
+    h = grid[1] - grid[0]
+    C = G._ab_coefficients(grid, lambda a, b: np.ones_like(a), lambda a: np.ones_like(a), 3)
+    assert np.allclose(C[0, :1], [h], rtol=1e-3) and np.allclose(C[1, :2], [1.5 * h, -0.5 * h], rtol=1e-3)
+    assert np.allclose(C[2, :3], np.array([23, -16, 5]) * h / 12, rtol=1e-3)
+    assert np.allclose(C[5], np.array([55, -59, 37, -9]) * h / 24, rtol=1e-3)
+    assert np.allclose(O.deis_rho_ab_coefficients(grid, 3), C, rtol=1e-12, atol=1e-15)
+    # Runge-Kutta tableaus: consistency conditions
+    for name, (c, a, b) in G.RK_TABLEAUS.items():
+        assert abs(sum(b) - 1) < 1e-12, name
+        for ci, row in zip(c, a):
+            assert abs(ci - sum(row)) < 1e-12, name
+    # the t_ab special case is the generator that reproduces the shipped results/deis matrices
+    a, b = G.deis_triple(10, "t_ab"), G._deis_tab_on(G._DeisVP().rev_ts(10), 3, 10000)
+    assert np.abs(a.A - b.A).max() < 1e-14
+    # time grids agree between product and oracle
+    for phase in ("t", "rho", "log"):
+        assert np.allclose(G._DeisVP().rev_ts(10, 2, phase), O.deis_rev_ts(10, 2, phase), rtol=1e-12)
+
+
+def test_third_order_solvers_converge_faster_than_first_order():
+    """sanity of the whole family on a Gaussian-data problem with a closed-form eps: x0 ~ N(0, s^2) => eps(x,t) linear in x"""
+    s2 = 0.25
+    vp = G.VPLinearSchedule()
+
+    def final_std(t):  # std of x_K when x_T ~ N(0,1): |sum of the linear map| -- exact answer is sqrt(alpha0^2 s2 + sigma0^2)
+        al, sg = t.node[:, 1], t.node[:, 2]
+        x, x0s = 1.0, []
+        for k in range(t.K):
+            eps = sg[k] * x / (al[k] ** 2 * s2 + sg[k] ** 2)
+            x0s.append((x - sg[k] * eps) / al[k])
+            x = sum(t.A[k, j] * x0s[j] for j in range(k + 1)) + t.B[k, 0] * 1.0
+        return abs(x)
+
+    # the initial state of the true process has variance alpha_T^2 s2 + sigma_T^2 (not 1): compare against the exact flow of x_T = 1
+    def exact(t_end=1e-3):
+        v = lambda t: vp.alpha(t) ** 2 * s2 + vp.sigma(t) ** 2
+        return np.sqrt(v(t_end) / v(1.0))
+
+    errs = {name: abs(final_std(t) - exact()) for name, t in
+            dict(o1=G.dpm_solver_triple(15, "dpmsolver++", "multistep", 1), o2=G.dpm_solver_triple(15, "dpmsolver++", "multistep", 2),
+                 o3=G.dpm_solver_triple(15, "dpmsolver++", "multistep", 3), rk=G.deis_triple(5, "rho_rk"), ab=G.deis_triple(15, "rho_ab")).items()}
+    assert errs["o3"] < errs["o2"] < errs["o1"] and errs["rk"] < errs["o1"] and errs["ab"] < errs["o1"], errs
