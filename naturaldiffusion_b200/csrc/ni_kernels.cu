@@ -39,6 +39,9 @@ std::atomic<int> g_tma_max_stages{32};
 std::atomic<int> g_tma_warps{8};
 std::atomic<int> g_tma_smem_kb{200};
 std::atomic<int> g_tma_ctas_per_sm{2};
+std::atomic<int> g_tma_tile_kb{2};   // bytes per source per stage: 2 or 4 KB
+std::atomic<int> g_tma_l2_hint{0};   // cp.async.bulk L2 cache hint: 0 none, 1 evict_first, 2 evict_last, 3 evict_normal
+std::atomic<int> g_tma_dynamic{0};   // 1: tiles claimed from a global counter instead of blockIdx.x + q * gridDim.x
 std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernels
 std::atomic<int> g_load_policy{0};   // step-kernel load flavour: 0 by launch footprint vs L2, 1 always L2-friendly (NA), 2 always streaming
 } // namespace
@@ -262,20 +265,22 @@ __global__ void __launch_bounds__(NI_BLOCK, NI_MIN_BLOCKS) ni_step_kernel(const 
 }
 
 // ---- variant 2: TMA bulk copies into a shared-memory ring, warp-specialised -------------------------
-// Persistent CTAs (one per SM by default): a producer warp streams [source][tile] slabs global->shared with
-// cp.async.bulk (one lane per source tensor, completion counted on an mbarrier), NW consumer warps each own
-// whole tiles (TMA_TILE_BYTES per source = 4 vectors per lane), so consumer warps run decoupled from each
-// other with 4 independent accumulation chains per thread.  A consumer reads the stored terms from shared
-// memory, runs the same epilogue as the direct-load kernel (reading out0/out1/x_k from shared memory when it
-// needs them), stores straight to global and hands the stage back.  stages x n_src x 2 KB (<= ~200 KB) of
-// loads are in flight per SM regardless of register pressure.  Source order in a stage: out0, [out1], [x_k],
-// term 0..n-1.
-constexpr int TMA_TILE_BYTES = 2048;
-constexpr int TMA_VPL = TMA_TILE_BYTES / 16 / 32; // vectors per consumer lane per tile
+// Persistent CTAs: a producer warp streams [source][tile] slabs global->shared with cp.async.bulk (one lane per
+// source tensor, completion counted on an mbarrier, optional L2 cache-hint operand), NW consumer warps each own whole
+// tiles (TILE_BYTES per source = 4 or 8 vectors per lane), so consumer warps run decoupled from each other with 4 / 8
+// independent accumulation chains per thread.  A consumer reads the stored terms from shared memory, runs the same
+// epilogue as the direct-load kernels (reading out0/out1/x_k from shared memory when it needs them), stores straight to
+// global and hands the stage back.  stages x n_src x TILE_BYTES (<= ~200 KB) of loads are in flight per SM regardless of
+// register pressure.  Source order in a stage: out0, [out1], [x_k], term 0..n-1.
+// Tiles are handed out statically (tile = blockIdx.x + q * gridDim.x) or, with "tma_dynamic", claimed from a global
+// counter by the producer (atomicInc that wraps after ntiles + gridDim claims: the counter is back at 0 when the grid
+// ends, no per-launch reset), the claimed index travelling to the consumers in shared memory next to the stage.
 constexpr int TMA_MAX_WARPS = 16;
 constexpr int TMA_MAX_STAGES = 32;
 constexpr int TMA_MAX_SRC = 32;
-constexpr int TMA_BAR_BYTES = 2 * TMA_MAX_STAGES * 8;
+constexpr int TMA_BAR_BYTES = 2 * TMA_MAX_STAGES * 8 + TMA_MAX_STAGES * 4; // full + empty barriers, claimed tile per stage
+constexpr int TMA_COUNTERS = 64;
+__device__ unsigned int g_tma_tile_counter[TMA_COUNTERS]; // zero-initialised; each launch uses one slot (rotating)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -288,19 +293,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile("{\n.reg .pred P1;\nNI_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra NI_DONE;\nbra NI_WAIT;\nNI_DONE:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+// L2 eviction-priority policies for the bulk copies (the encodings CUTLASS ships as TMA::CacheHintSm90)
+constexpr uint64_t TMA_HINT[4] = {0ull, 0x12F0000000000000ull /* evict_first */, 0x14F0000000000000ull /* evict_last */, 0x1000000000000000ull /* evict_normal */};
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t hint)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    if (hint == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(hint) : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<32> tab, int n_src, int stages, int64_t ntiles)
+template <typename T, int TILE_BYTES>
+__global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kernel(const __grid_constant__ StepArgs s, const __grid_constant__ TermTable<32> tab, int n_src, int stages, int64_t ntiles,
+                                                                                      uint64_t l2_hint, int counter_slot /* < 0: static tiles */)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int TILE_ELEMS = TMA_TILE_BYTES / (int)sizeof(T);
+    constexpr int TILE_ELEMS = TILE_BYTES / (int)sizeof(T);
+    constexpr int VPL = TILE_BYTES / 16 / 32; // vectors per consumer lane per tile
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + TMA_MAX_STAGES;
+    int *stage_tile = reinterpret_cast<int *>(empty + TMA_MAX_STAGES);
     unsigned char *tiles = smem + TMA_BAR_BYTES;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -310,6 +323,7 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
     const bool has_x = has_x0 && s.x_in != nullptr;
     const bool has_o1 = has_x0 && s.out1 != nullptr;
     const int n_pre = has_x0 ? 1 + (has_o1 ? 1 : 0) + (has_x ? 1 : 0) : 0; // sources ahead of the terms
+    const bool dynamic = counter_slot >= 0;
 
     if (tid == 0) {
         for (int st = 0; st < stages; ++st) {
@@ -335,57 +349,80 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
         }
         int st = 0;
         uint32_t ph = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t e0 = tile * TILE_ELEMS;
-            const int64_t rem = numel - e0;
-            const uint32_t bytes = (uint32_t)((rem < TILE_ELEMS ? rem : TILE_ELEMS) * (int64_t)sizeof(T));
-            if (lane == 0) {
-                mbar_wait(&empty[st], ph ^ 1u);
-                mbar_expect_tx(&full[st], bytes * (uint32_t)n_src);
-            }
-            __syncwarp();
-            if (lane < n_src) {
-                int64_t off = e0;
-                if (is_out && s.out_strided) { // tiles never straddle samples (host guarantees per_sample % TILE_ELEMS == 0)
-                    const int64_t smp = e0 / s.per_sample;
-                    off = smp * s.out_sample_stride + (e0 - smp * s.per_sample);
+        int sentinels = 0;
+        for (int64_t q = 0;; ++q) {
+            int64_t tile;
+            if (dynamic) {
+                if (sentinels > 0) tile = ntiles;
+                else {
+                    unsigned int c = 0;
+                    if (lane == 0) c = atomicInc(&g_tma_tile_counter[counter_slot], (unsigned int)(ntiles + gridDim.x - 1));
+                    tile = (int64_t)__shfl_sync(0xffffffffu, c, 0);
                 }
-                bulk_g2s(tiles + ((size_t)st * n_src + lane) * TMA_TILE_BYTES, gbase + off * (int64_t)sizeof(T), bytes, &full[st]);
+            } else {
+                tile = blockIdx.x + q * (int64_t)gridDim.x;
+            }
+            const bool done = tile >= ntiles;
+            if (done && !dynamic) break;
+            if (lane == 0) mbar_wait(&empty[st], ph ^ 1u);
+            __syncwarp();
+            if (done) {
+                // tell one consumer warp that the tiles are gone; every consumer warp needs its own notice
+                if (lane == 0) { stage_tile[st] = -1; mbar_arrive(&full[st]); }
+                if (++sentinels == nw) break;
+            } else {
+                const int64_t e0 = tile * TILE_ELEMS;
+                const int64_t rem = numel - e0;
+                const uint32_t bytes = (uint32_t)((rem < TILE_ELEMS ? rem : TILE_ELEMS) * (int64_t)sizeof(T));
+                if (lane == 0) {
+                    stage_tile[st] = (int)tile;
+                    mbar_expect_tx(&full[st], bytes * (uint32_t)n_src);
+                }
+                __syncwarp();
+                if (lane < n_src) {
+                    int64_t off = e0;
+                    if (is_out && s.out_strided) { // tiles never straddle samples (host guarantees per_sample % TILE_ELEMS == 0)
+                        const int64_t smp = e0 / s.per_sample;
+                        off = smp * s.out_sample_stride + (e0 - smp * s.per_sample);
+                    }
+                    bulk_g2s(tiles + ((size_t)st * n_src + lane) * TILE_BYTES, gbase + off * (int64_t)sizeof(T), bytes, &full[st], l2_hint);
+                }
             }
             if (++st == stages) { st = 0; ph ^= 1u; }
         }
     } else {
-        // ---------------- consumer warp `warp` owns tiles it = warp, warp + nw, ... of this CTA's sequence
+        // ---------------- consumer warp `warp` owns stage-sequence numbers it = warp, warp + nw, ... of this CTA
         const int n = s.n_terms;
         for (int64_t it = warp;; it += nw) {
-            const int64_t tile = blockIdx.x + it * (int64_t)gridDim.x;
-            if (tile >= ntiles) break;
+            if (!dynamic && blockIdx.x + it * (int64_t)gridDim.x >= ntiles) break;
             const int st = (int)(it % stages);
             const uint32_t ph = (uint32_t)((it / stages) & 1);
-            const int64_t e_tile = tile * TILE_ELEMS;
             mbar_wait(&full[st], ph);
-            const unsigned char *sp = tiles + (size_t)st * n_src * TMA_TILE_BYTES + lane * 16;
+            const int64_t tile = stage_tile[st];
+            if (tile < 0) break;
+            const int64_t e_tile = tile * TILE_ELEMS;
+            const unsigned char *sp = tiles + (size_t)st * n_src * TILE_BYTES + lane * 16;
             auto lds = [&](int src, int v) {
-                const uint4 q = *reinterpret_cast<const uint4 *>(sp + (size_t)src * TMA_TILE_BYTES + v * 512);
+                const uint4 q = *reinterpret_cast<const uint4 *>(sp + (size_t)src * TILE_BYTES + v * 512);
                 Raw<T, VEC> r;
                 r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
                 return r;
             };
-            float acc[TMA_VPL][VEC];
+            float acc[VPL][VEC];
 #pragma unroll
-            for (int v = 0; v < TMA_VPL; ++v)
+            for (int v = 0; v < VPL; ++v)
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[v][i] = 0.f;
             for (int t = 0; t < n; ++t) {
                 const float c = tab.c[t];
-                Raw<T, VEC> rr[TMA_VPL];
+                Raw<T, VEC> rr[VPL];
 #pragma unroll
-                for (int v = 0; v < TMA_VPL; ++v) rr[v] = lds(n_pre + t, v);
+                for (int v = 0; v < VPL; ++v) rr[v] = lds(n_pre + t, v);
 #pragma unroll
-                for (int v = 0; v < TMA_VPL; ++v) fma_term<T, VEC>(acc[v], rr[v], c);
+                for (int v = 0; v < VPL; ++v) fma_term<T, VEC>(acc[v], rr[v], c);
             }
 #pragma unroll
-            for (int v = 0; v < TMA_VPL; ++v) {
+            for (int v = 0; v < VPL; ++v) {
                 const int64_t e = e_tile + (int64_t)(v * 32 + lane) * VEC;
                 if (e < numel) {
                     Raw<T, VEC> rx, ro0, ro1;
@@ -593,59 +630,61 @@ int launch_step_cap(const StepArgs &a, const NiStepDesc *d, cudaStream_t st)
 int sm_count() { return dev_info().sms; }
 
 // TMA variant: eligible when the row fits one shared-memory stage set and tiles map 1:1 onto sources
-template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cudaStream_t st, bool *used)
+template <typename T, int TILE_BYTES> int launch_step_tma_tile(StepArgs &a, const NiStepDesc *d, cudaStream_t st, bool *used)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int TILE_ELEMS = TMA_TILE_BYTES / (int)sizeof(T);
+    constexpr int TILE_ELEMS = TILE_BYTES / (int)sizeof(T);
     *used = false;
     const int n_pre = d->has_x0 ? 1 + (d->out1 != nullptr ? 1 : 0) + (a.x_in != nullptr ? 1 : 0) : 0;
     const int n_src = n_pre + d->n_terms;
     if (n_src < 1 || n_src > TMA_MAX_SRC || d->n_terms > 32 || d->accumulate) return NI_OK;
     if (a.out_strided && d->per_sample % TILE_ELEMS != 0) return NI_OK;
+    const int64_t ntiles = (d->numel + TILE_ELEMS - 1) / TILE_ELEMS;
+    if (ntiles >= (1ll << 31) - 4096) return NI_OK;
     const int ctas = g_tma_ctas_per_sm.load();
     int nw = g_tma_warps.load();
     const int budget = g_tma_smem_kb.load() * 1024 / ctas - TMA_BAR_BYTES;
-    int stages = budget / (n_src * TMA_TILE_BYTES);
+    int stages = budget / (n_src * TILE_BYTES);
     if (stages > g_tma_max_stages.load()) stages = g_tma_max_stages.load();
     if (stages > TMA_MAX_STAGES) stages = TMA_MAX_STAGES;
     if (stages < 2) return NI_OK;
     if (nw > stages) nw = stages;      // a consumer warp without a stage of its own would only wait
-    // Stage of tile `it` is it % stages, its consumer is warp it % nw.  stages must be a multiple of nw so that every
+    // Stage of sequence number `it` is it % stages, its consumer is warp it % nw.  stages must be a multiple of nw so that every
     // barrier has ONE waiter walking its phases in order: mbarrier parity waits only tell the current phase from the
     // previous one, and with an unaligned ring a warp running ahead would wait on a phase two steps in the future, get
     // the stale parity of the preceding phase, read an unfilled stage and release it early (observed: launch failure).
     stages -= stages % nw;
-    const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TMA_TILE_BYTES;
+    const size_t smem = TMA_BAR_BYTES + (size_t)stages * n_src * TILE_BYTES;
     static thread_local int attr_dev = -1; // the opt-in is per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != attr_dev) {
-        cudaError_t err = cudaFuncSetAttribute(ni_step_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t err = cudaFuncSetAttribute(ni_step_tma_kernel<T, TILE_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (err != cudaSuccess) return fail(NI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
         attr_dev = dev;
     }
     a.nvec = d->numel / VEC;
-    const int64_t ntiles = (d->numel + TILE_ELEMS - 1) / TILE_ELEMS;
     int64_t grid = (int64_t)sm_count() * ctas;
     if (grid > ntiles) grid = ntiles;
     TermTable<32> tab;
     memset(&tab, 0, sizeof(tab));
     for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3((unsigned)((nw + 1) * 32));
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 0; // measured: PDL slows the persistent kernel down (profiles/r01_sweep.txt)
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, ni_step_tma_kernel<T>, a, tab, n_src, stages, ntiles);
-    }
+    static std::atomic<unsigned> next_slot{0};
+    const int slot = g_tma_dynamic.load() ? (int)(next_slot.fetch_add(1) % TMA_COUNTERS) : -1;
+    const uint64_t hint = TMA_HINT[g_tma_l2_hint.load() & 3];
+    launch_pdl(ni_step_tma_kernel<T, TILE_BYTES>, (unsigned)grid, (unsigned)((nw + 1) * 32), smem, st,
+               false /* measured: PDL slows the persistent kernel down (profiles/r01_sweep.txt) */, a, tab, n_src, stages, ntiles, hint, slot);
     *used = true;
     return check_launch("ni_step (TMA) launch");
+}
+
+template <typename T> int launch_step_tma(StepArgs &a, const NiStepDesc *d, cudaStream_t st, bool *used)
+{
+    if (g_tma_tile_kb.load() == 4) {
+        const int rc = launch_step_tma_tile<T, 4096>(a, d, st, used);
+        if (rc != NI_OK || *used) return rc;
+    }
+    return launch_step_tma_tile<T, 2048>(a, d, st, used);
 }
 
 template <typename T, typename TO> int launch_step(StepArgs &a, const NiStepDesc *d, bool vec_ok, cudaStream_t st)
@@ -692,6 +731,9 @@ int ni_set_option(const char *name, int value)
     if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NI_OK; }
     if (!strcmp(name, "load_policy")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "load_policy must be 0..2"); g_load_policy = value; return NI_OK; }
+    if (!strcmp(name, "tma_tile_kb")) { if (value != 2 && value != 4) return fail(NI_ERR_INVALID, "tma_tile_kb must be 2 or 4"); g_tma_tile_kb = value; return NI_OK; }
+    if (!strcmp(name, "tma_l2_hint")) { if (value < 0 || value > 3) return fail(NI_ERR_INVALID, "tma_l2_hint must be 0..3"); g_tma_l2_hint = value; return NI_OK; }
+    if (!strcmp(name, "tma_dynamic")) { g_tma_dynamic = value ? 1 : 0; return NI_OK; }
     if (!strcmp(name, "tma_ctas_per_sm")) { if (value < 1 || value > 4) return fail(NI_ERR_INVALID, "tma_ctas_per_sm must be 1..4"); g_tma_ctas_per_sm = value; return NI_OK; }
     return fail(NI_ERR_INVALID, "ni_set_option: unknown option '%s'", name);
 }

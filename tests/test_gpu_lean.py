@@ -160,3 +160,36 @@ def test_c5_full_latent_16x128x128_matches_oracle(weights_dir, table, dt, tol, m
     ref, _ = O.sd3_ni_loop(W, sig, model, noise.to(dt).float())
     ref = ref * fs + fb
     assert rel_err(got.float(), ref) < tol
+
+
+@pytest.mark.parametrize("opts", [dict(tma_tile_kb=4), dict(tma_l2_hint=1), dict(tma_l2_hint=2, tma_tile_kb=4), dict(tma_dynamic=1),
+                                  dict(tma_dynamic=1, tma_tile_kb=4, tma_warps=16, tma_ctas_per_sm=1), dict(tma_l2_hint=3, tma_dynamic=1)])
+@pytest.mark.parametrize("dt,shape,cout,ncond", [(torch.float32, (33, 3, 32, 32), 3, 1), (torch.float16, (5, 4, 32, 32), 8, 2), (torch.float32, (1, 1, 1, 1000), 1, 1),
+                                                 (torch.float32, (600, 3, 32, 32), 3, 1)])
+def test_tma_knobs_are_bit_identical(opts, dt, shape, cout, ncond):
+    """4 KB tiles, the L2 cache-hint operand of cp.async.bulk and dynamic tile claiming (self-resetting atomicInc counter)
+    change scheduling only: same bits as the generic direct-load kernel, launch after launch (the counter must be back at
+    zero each time)"""
+    g = torch.Generator().manual_seed(sum(shape) + cout)
+    mk = lambda *s_: torch.randn(*s_, generator=g).to(dt).to(DEV)
+    B, C, H, W = shape
+    kw = dict(x_in=mk(*shape), outs=[mk(B, cout, H, W) for _ in range(ncond)], a=1.3, b=[-0.7, 0.2][:ncond], c_x0=0.8,
+              terms=[(0.1 * (i + 1) * (-1) ** i, mk(*shape)) for i in range(6)], gens=[(0.3, 5)], seed=9, keep_gen=[True],
+              per_sample=C * H * W, out_sample_stride=cout * H * W, want_sumsq=True)
+    defaults = dict(tma_tile_kb=2, tma_l2_hint=0, tma_dynamic=0, tma_warps=8, tma_ctas_per_sm=2)
+    try:
+        _lib.set_option("variant", 1)
+        ref = fused_step(**kw)
+        _lib.set_option("variant", 2)
+        for k, v in {**defaults, **opts}.items():
+            _lib.set_option(k, v)
+        for _ in range(3):
+            got = fused_step(**kw)
+            for key in ("x_next", "x0"):
+                assert torch.equal(got[key], ref[key]), key
+            assert torch.equal(got["gen"][0], ref["gen"][0])
+            assert torch.allclose(got["sumsq"], ref["sumsq"], rtol=1e-5)
+    finally:
+        _lib.set_option("variant", 0)
+        for k, v in defaults.items():
+            _lib.set_option(k, v)

@@ -42,7 +42,7 @@ def rel_err(got, ref):
 def test_library_loaded_is_in_tree():
     from naturaldiffusion_b200 import _lib
     assert os.path.samefile(os.path.dirname(_lib.LIB_PATH), os.path.dirname(_lib.__file__))
-    assert ni.lib().ni_version() == 3
+    assert ni.lib().ni_version() == _lib.NI_ABI_VERSION == 4
 
 
 @pytest.mark.parametrize("numel,off", [(4096, 0), (4100, 0), (1000, 4), (1001, 7), (5, 1), (1 << 20, 1 << 33)])
