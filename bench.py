@@ -461,6 +461,87 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
     return e2e
 
 
+def fid_arm(ctx):
+    """The evaluation step behind the sampler: fp64 sufficient statistics of 2048-d activations on the fp64
+    tensor cores (csrc/ni_fid.cu) and, at N > 1, the ONE collective of the north-star -- the all-reduce of the 34 MB
+    statistics buffer over NCCL."""
+    from naturaldiffusion_b200.fid import FidAccumulator
+    torch = ctx.torch
+    m, d = 8192, 2048
+    x = torch.randn(m, d, device=ctx.dev)
+    acc = FidAccumulator(dim=d, device=ctx.dev)
+    for _ in range(2):
+        acc.update(x)
+    ctx.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        acc.update(x)
+    b.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(a.elapsed_time(b)) / 5
+    out = {"activations": [m, d], "ms_per_update": ms, "fp64_tflops_symmetric": m * d * (d + 1.0) / ms / 1e9,
+           "fp64_tflops_full_gemm_equivalent": 2.0 * m * d * d / ms / 1e9, "images_per_s": ctx.world * m / (ms * 1e-3),
+           "kernel": "ni_fid_syrk_kernel (DMMA m8n8k4, upper-triangular 64x64 tiles + mirror) + ni_fid_colsum_kernel"}
+    if ctx.world > 1:
+        acc.all_reduce()
+        ctx.barrier()
+        a.record()
+        for _ in range(5):
+            acc.all_reduce()
+        b.record()
+        ctx.barrier()
+        ar = ctx.max_over_ranks(a.elapsed_time(b)) / 5
+        nbytes = acc.buf.numel() * 8
+        out["allreduce"] = {"bytes": nbytes, "ms": ar, "bus_gbs": 2.0 * (ctx.world - 1) / ctx.world * nbytes / (ar * 1e-3) / 1e9, "ranks": ctx.world,
+                            "what": "torch.distributed.all_reduce(SUM) of [n | sum x | sum x x^T] fp64 over NCCL, once per evaluated set"}
+    return out
+
+
+def samplers_via_matrix(ctx, batch=4096):
+    """"Original sampler vs Natural Inference" on ONE code path: 15-model-call samplers on the CIFAR shape, each as its
+    coefficient matrix through the same fused step kernel with the null denoiser -- the reference's optimised banded
+    matrix next to the (dense) matrices of the original solvers that head results/FID/*_15step.csv."""
+    import naturaldiffusion_b200 as ni
+    from naturaldiffusion_b200 import generators as G
+    from naturaldiffusion_b200.ops import philox_normal
+    from naturaldiffusion_b200.sampler import NaturalInferenceSampler
+    torch = ctx.torch
+    shape = (3, 32, 32)
+    out_t = philox_normal((batch,) + shape, seed=888, tensor_id=1000, device=ctx.dev)
+    noise = philox_normal((batch,) + shape, seed=888, tensor_id=0, device=ctx.dev)
+    den = lambda x, k: out_t
+    cases = [("NI optimised step_15_weight_173", ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, "step_15_weight_173.npz"))),
+             ("DPM-Solver++ multistep-2 (2M)", G.dpm_solver_triple(15, "dpmsolver++", "multistep", 2)),
+             ("DPM-Solver++ multistep-3", G.dpm_solver_triple(15, "dpmsolver++", "multistep", 3)),
+             ("DPM-Solver multistep-3", G.dpm_solver_triple(15, "dpmsolver", "multistep", 3)),
+             ("DPM-Solver++ singlestep-3", G.dpm_solver_triple(15, "dpmsolver++", "singlestep", 3)),
+             ("DEIS tAB3", G.deis_triple(15, "t_ab")), ("DEIS rhoAB3", G.deis_triple(15, "rho_ab")), ("DEIS iPNDM", G.deis_triple(15, "ipndm")),
+             ("DEIS rhoRK-3kutta (5 steps x 3 calls)", G.deis_triple(5, "rho_rk")),
+             ("DDIM-15 (first-order path)", G.ddim_triple(15))]
+    res = []
+    for name, t in cases:
+        io = ni.io_score_vp(t.node) if t.node[0, 0] <= 1.0 else ni.io_eps_cfg(*ni.coeffs.ddim_x0_coeffs(15)[:2], None)
+        s = NaturalInferenceSampler(t, io, batch, shape, device=ctx.dev, seed=888)
+        s.capture(den, noise=noise)
+        for _ in range(5):
+            s.replay()
+        torch.cuda.synchronize()
+        n = 40
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            s.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / n
+        units = s.plan.total_units(1)
+        res.append({"sampler": name, "K": t.K, "ms_per_trajectory": ms, "tensor_transfers": units, "x0_ring_slots": s.plan.n_x0_slots,
+                    "first_order_path": bool(s.plan.markov), "achieved_gbs": units * s.numel * 4 / ms / 1e6, "samples_per_s": batch / (ms * 1e-3)})
+        del s
+    return res
+
+
 def cross_rank_check(ctx):
     """N > 1: prove bits, not just speed.  (i) every rank hashes the x_K of its shard of one global batch (deterministic C2
     matrix, in-kernel initial noise) and of a stochastic DDPM-20 run (in-kernel fresh noise every step); rank 0 recomputes
@@ -611,6 +692,12 @@ def run_ours(args, rank, world, local_rank):
 
     if world > 1 and not args.no_check:
         line["multi_gpu_check"] = cross_rank_check(ctx)
+    if not args.no_per_config and args.config == "c2":
+        del w
+        torch.cuda.empty_cache()
+        line["fid"] = fid_arm(ctx)
+        if world == 1:
+            line["samplers_via_matrix"] = samplers_via_matrix(ctx)
 
     if rank != 0:
         if world > 1:

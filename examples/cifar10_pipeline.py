@@ -38,7 +38,7 @@ def feature_net(dim, device):
     return net.to(device).eval()
 
 
-def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, seed=888, small_model=False, quiet=False):
+def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, seed=888, small_model=False, quiet=False, features="small"):
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
@@ -48,7 +48,12 @@ def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, 
     torch.manual_seed(0)
     model = (NCSNppVP(nf=32, num_res_blocks=1) if small_model else NCSNppVP()).reinit_output().to(dev).eval()
     den = ncsnpp_denoiser(model, triple.node)
-    feats = feature_net(feat_dim, dev)
+    if features == "inception":   # the reference's evaluation shape: 2048-d pool3 activations of an InceptionV3 (random-init offline)
+        from naturaldiffusion_b200.fid import inception_pool3_standin
+        feat_dim = 2048
+        feats = inception_pool3_standin(dev, torch.bfloat16)
+    else:
+        feats = feature_net(feat_dim, dev)
     lo, hi = shard_range(samples, rank, world)                      # this rank's samples [lo, hi) of the global run
     acc = FidAccumulator(dim=feat_dim, device=dev)
     t0 = time.perf_counter()
@@ -62,15 +67,19 @@ def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, 
         pix = torch.empty((b, 32, 32, 3), dtype=torch.uint8, device=dev)
         s.sample(den, pixels_out=pix)                                 # K fused steps, last one emits uint8 NHWC
         accumulate_images(acc, pix, feats, batch_size=b)
+    torch.cuda.synchronize()
+    t_ar = time.perf_counter()
     acc.all_reduce()                                                   # the only collective
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    ar_ms = (time.perf_counter() - t_ar) * 1e3
     mu, sigma = acc.finalize()
     rng = np.random.default_rng(0)                                     # stand-in for weights/cifar10_mu_sigma.npz
     ref = rng.standard_normal((4 * feat_dim, feat_dim)) * 0.05 + mu
     fid = frechet_distance(np.mean(ref, 0), np.cov(ref, rowvar=False), mu, sigma)
     if rank == 0 and not quiet:
         print(f"{samples} samples on {world} GPU(s) in {dt:.2f} s ({samples / dt:.0f} samples/s incl. random-init NCSN++); "
+              f"features={features} ({feat_dim}-d); all-reduce of {acc.buf.numel() * 8 / 1e6:.1f} MB statistics {ar_ms:.2f} ms; "
               f"n={int(acc.n)}; plumbing-only FID vs synthetic statistics = {fid:.4f}")
     return dict(n=acc.n, mu=mu, sigma=sigma, fid=fid, seconds=dt)
 
@@ -81,7 +90,8 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=500)
     ap.add_argument("--weights", default="step_10_weight_42.npz")
     ap.add_argument("--small-model", action="store_true")
+    ap.add_argument("--features", default="small", choices=["small", "inception"], help="inception: torchvision InceptionV3 (random init), 2048-d pool3")
     a = ap.parse_args()
-    run(a.samples, a.batch, a.weights, small_model=a.small_model)
+    run(a.samples, a.batch, a.weights, small_model=a.small_model, features=a.features)
     if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()

@@ -450,7 +450,9 @@ template <int CAP> struct WsumTable {
     double c[CAP];
 };
 
-template <typename TS, typename TD, int VEC, int CAP>
+// POL: load flavour, picked per launch like the step kernels' (plain ld.global when the call streams far more than the L2
+// holds, L1::no_allocate when what it writes can stay resident for the next reader)
+template <typename TS, typename TD, int VEC, int CAP, int POL>
 __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant__ WsumTable<CAP> tab, int n, void *dst, int64_t nvec, double scale)
 {
     const int64_t v = (int64_t)blockIdx.x * NI_BLOCK + threadIdx.x;
@@ -462,17 +464,18 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.0;
         int t = 0;
-        for (; t + 4 <= n; t += 4) {
-            Raw<double, VEC> rr[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rr[j] = load_raw<double, VEC>(static_cast<const double *>(tab.ptr[t + j]) + e);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) acc[i] = fma(tab.c[t + j], __hiloint2double(rr[j].w[2 * i + 1], rr[j].w[2 * i]), acc[i]);
-        }
+#define NI_WSUM64_BATCH(NB)                                                                                                              \
+    for (; t + NB <= n; t += NB) {                                                                                                       \
+        Raw<double, VEC> rr[NB];                                                                                                         \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<double, VEC, POL>(static_cast<const double *>(tab.ptr[t + j]) + e); \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j)                                                                                   \
+            _Pragma("unroll") for (int i = 0; i < VEC; ++i) acc[i] = fma(tab.c[t + j], __hiloint2double(rr[j].w[2 * i + 1], rr[j].w[2 * i]), acc[i]); \
+    }
+        NI_WSUM64_BATCH(8)
+        NI_WSUM64_BATCH(4)
+#undef NI_WSUM64_BATCH
         for (; t < n; ++t) {
-            Raw<double, VEC> r1 = load_raw<double, VEC>(static_cast<const double *>(tab.ptr[t]) + e);
+            Raw<double, VEC> r1 = load_raw<double, VEC, POL>(static_cast<const double *>(tab.ptr[t]) + e);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = fma(tab.c[t], __hiloint2double(r1.w[2 * i + 1], r1.w[2 * i]), acc[i]);
         }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant
         for (; t + 8 <= n; t += 8) {
             Raw<TS, VEC> rr[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = load_raw<TS, VEC>(static_cast<const TS *>(tab.ptr[t + j]) + e);
+            for (int j = 0; j < 8; ++j) rr[j] = load_raw<TS, VEC, POL>(static_cast<const TS *>(tab.ptr[t + j]) + e);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float f[VEC];
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(NI_BLOCK) ni_wsum_kernel(const __grid_constant
         }
         for (; t < n; ++t) {
             float f[VEC];
-            unpack<TS, VEC>(load_raw<TS, VEC>(static_cast<const TS *>(tab.ptr[t]) + e), f);
+            unpack<TS, VEC>(load_raw<TS, VEC, POL>(static_cast<const TS *>(tab.ptr[t]) + e), f);
             const float c = (float)tab.c[t];
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = fmaf(c, f[i], acc[i]);
@@ -819,8 +822,8 @@ int ni_step(const NiStepDesc *d, void *stream)
 } // extern "C"
 
 namespace {
-template <typename TS, typename TD>
-int launch_wsum(const void *const *src, const double *coeffs, int n, void *dst, int64_t numel, double scale, bool vec_ok, cudaStream_t st)
+template <typename TS, typename TD, int POL>
+int launch_wsum_pol(const void *const *src, const double *coeffs, int n, void *dst, int64_t numel, double scale, bool vec_ok, cudaStream_t st)
 {
     static thread_local WsumTable<NI_MAX_TERMS> big;
     constexpr int VEC = 16 / (int)sizeof(TS);
@@ -830,20 +833,31 @@ int launch_wsum(const void *const *src, const double *coeffs, int n, void *dst, 
         for (int i = 0; i < n; ++i) { tab.ptr[i] = src[i]; tab.c[i] = coeffs[i]; }
         if (vec_ok) {
             const int64_t nvec = numel / VEC;
-            ni_wsum_kernel<TS, TD, VEC, 32><<<(unsigned)((nvec + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(tab, n, dst, nvec, scale);
+            ni_wsum_kernel<TS, TD, VEC, 32, POL><<<(unsigned)((nvec + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(tab, n, dst, nvec, scale);
         } else {
-            ni_wsum_kernel<TS, TD, 1, 32><<<(unsigned)((numel + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(tab, n, dst, numel, scale);
+            ni_wsum_kernel<TS, TD, 1, 32, NI_LOAD_POLICY><<<(unsigned)((numel + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(tab, n, dst, numel, scale);
         }
     } else {
         for (int i = 0; i < n; ++i) { big.ptr[i] = src[i]; big.c[i] = coeffs[i]; }
         if (vec_ok) {
             const int64_t nvec = numel / VEC;
-            ni_wsum_kernel<TS, TD, VEC, NI_MAX_TERMS><<<(unsigned)((nvec + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(big, n, dst, nvec, scale);
+            ni_wsum_kernel<TS, TD, VEC, NI_MAX_TERMS, POL><<<(unsigned)((nvec + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(big, n, dst, nvec, scale);
         } else {
-            ni_wsum_kernel<TS, TD, 1, NI_MAX_TERMS><<<(unsigned)((numel + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(big, n, dst, numel, scale);
+            ni_wsum_kernel<TS, TD, 1, NI_MAX_TERMS, NI_LOAD_POLICY><<<(unsigned)((numel + NI_BLOCK - 1) / NI_BLOCK), NI_BLOCK, 0, st>>>(big, n, dst, numel, scale);
         }
     }
     return check_launch("ni_weighted_sum launch");
+}
+
+template <typename TS, typename TD>
+int launch_wsum(const void *const *src, const double *coeffs, int n, void *dst, int64_t numel, double scale, bool vec_ok, cudaStream_t st)
+{
+    // same rule as launch_streams(): keep the L2-friendly loads only when the result fits in 0.6 of the L2 and is a visible share of the traffic
+    const int pol = g_load_policy.load(std::memory_order_relaxed);
+    const int64_t written = numel * (int64_t)sizeof(TD), read = (int64_t)n * numel * (int64_t)sizeof(TS);
+    const bool streams = pol != 0 ? pol == 2 : (NI_L2_KEEP_DEN * written > NI_L2_KEEP_NUM * dev_info().l2_bytes || NI_L2_KEEP_SHARE * written < read + written);
+    if (streams) return launch_wsum_pol<TS, TD, NI_STREAM_LOAD_POLICY>(src, coeffs, n, dst, numel, scale, vec_ok, st);
+    return launch_wsum_pol<TS, TD, NI_LOAD_POLICY>(src, coeffs, n, dst, numel, scale, vec_ok, st);
 }
 } // namespace
 

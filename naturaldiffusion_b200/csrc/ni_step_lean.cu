@@ -46,77 +46,44 @@ struct LeanArgs {
     int n_terms, n_gen, lp_dtype, accumulate;
 };
 
+// One vector (VEC elements) of one step: every load issued before the first FMA, the sum in table order, generated noise,
+// the x0 stage, the stores of x0_k / x_{k+1} / the low-precision copy.  Leaves x_{k+1} (fp32, before storage rounding) in acc.
 // NT >= 0: exactly NT stored terms, NG/M exact.  NT < 0: runtime n_terms / n_gen, M still exact.
-template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP>
-__global__ void __launch_bounds__(NI_BLOCK, (PIX ? 6 : (NG >= 1 && NT >= 6) ? 8 : NI_LEAN_MIN_BLOCKS)) ni_step_lean_kernel(const __grid_constant__ LeanArgs s, const __grid_constant__ TermTable<CAP> tab)
+template <typename T, typename TO, int NT, int NG, int M, int POL, int CAP>
+__device__ __forceinline__ void lean_vector(const LeanArgs &s, const TermTable<CAP> &tab, uint32_t v, uint32_t vo, float (&acc)[16 / (int)sizeof(T)])
 {
     constexpr int VEC = 16 / (int)sizeof(T);
-    constexpr int VPT = PIX ? 3 : 1; // vectors per thread
-    pdl_launch_dependents();
-
-    uint32_t v[VPT];
-    uint32_t sample = 0;
-    if constexpr (PIX) {
-        // thread g owns pixels [4q, 4q+4) of sample n in all three channel planes
-        const uint32_t g = blockIdx.x * NI_BLOCK + threadIdx.x;
-        if (g >= s.n_pix_threads) return; // host guarantees whole warps (hw_vec % 32 == 0)
-        sample = g / s.hw_vec;
-        const uint32_t q = g - sample * s.hw_vec;
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) v[i] = sample * s.vec_per_sample + i * s.hw_vec + q;
-    } else {
-        v[0] = blockIdx.x * NI_BLOCK + threadIdx.x;
-        if (v[0] >= s.nvec) return;
-        if (s.out_extra_vec != 0 || s.sumsq != nullptr) {
-            if (s.tile_in_sample) sample = s.tps_mul == 0 ? blockIdx.x : (__umulhi(blockIdx.x, s.tps_mul) >> s.tps_shr);
-            else sample = v[0] / s.vec_per_sample;
-        }
-    }
-    pdl_wait();
-
     const bool has_x = s.x_in != nullptr;
-    const uint32_t vo_extra = sample * s.out_extra_vec;
-
-    Raw<TO, VEC> ro0[VPT], ro1[VPT];
-    Raw<T, VEC> rx[VPT];
-    float acc[VPT][VEC];
+    Raw<TO, VEC> ro0, ro1;
+    Raw<T, VEC> rx;
+    ro0 = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out0) + (size_t)vo * VEC);
+    if constexpr (M == 2) ro1 = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out1) + (size_t)vo * VEC);
+    if (has_x) rx = load_raw<T, VEC, POL>(static_cast<const T *>(s.x_in) + (size_t)v * VEC);
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-        ro0[i] = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out0) + (size_t)(v[i] + vo_extra) * VEC);
-        if constexpr (M == 2) ro1[i] = load_raw<TO, VEC, POL>(static_cast<const TO *>(s.out1) + (size_t)(v[i] + vo_extra) * VEC);
-        if (has_x) rx[i] = load_raw<T, VEC, POL>(static_cast<const T *>(s.x_in) + (size_t)v[i] * VEC);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[i][j] = 0.f;
-    }
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
 
     // stored terms, table order
     if constexpr (NT >= 0) {
+        Raw<T, VEC> rr[NT > 0 ? NT : 1];
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            Raw<T, VEC> rr[NT > 0 ? NT : 1];
+        for (int t = 0; t < NT; ++t) rr[t] = load_raw<T, VEC, POL>(static_cast<const T *>(tab.ptr[t]) + (size_t)v * VEC);
 #pragma unroll
-            for (int t = 0; t < NT; ++t) rr[t] = load_raw<T, VEC, POL>(static_cast<const T *>(tab.ptr[t]) + (size_t)v[i] * VEC);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) fma_term<T, VEC>(acc[i], rr[t], tab.c[t]);
-        }
+        for (int t = 0; t < NT; ++t) fma_term<T, VEC>(acc, rr[t], tab.c[t]);
     } else {
         const int n = s.n_terms;
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            if (s.accumulate) unpack<T, VEC>(load_raw<T, VEC, POL>(static_cast<const T *>(s.x_next) + (size_t)v[i] * VEC), acc[i]);
-            int t = 0;
-#define NI_TERM_BATCH(NB)                                                                                                              \
-    for (; t + NB <= n; t += NB) {                                                                                                     \
-        Raw<T, VEC> rr[NB];                                                                                                            \
-        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC, POL>(static_cast<const T *>(tab.ptr[t + j]) + (size_t)v[i] * VEC); \
-        _Pragma("unroll") for (int j = 0; j < NB; ++j) fma_term<T, VEC>(acc[i], rr[j], tab.c[t + j]);                                  \
+        if (s.accumulate) unpack<T, VEC>(load_raw<T, VEC, POL>(static_cast<const T *>(s.x_next) + (size_t)v * VEC), acc);
+        int t = 0;
+#define NI_TERM_BATCH(NB)                                                                                                          \
+    for (; t + NB <= n; t += NB) {                                                                                                 \
+        Raw<T, VEC> rr[NB];                                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) rr[j] = load_raw<T, VEC, POL>(static_cast<const T *>(tab.ptr[t + j]) + (size_t)v * VEC); \
+        _Pragma("unroll") for (int j = 0; j < NB; ++j) fma_term<T, VEC>(acc, rr[j], tab.c[t + j]);                                 \
     }
-            NI_TERM_BATCH(8)
-            NI_TERM_BATCH(4)
-            NI_TERM_BATCH(2)
-            NI_TERM_BATCH(1)
+        NI_TERM_BATCH(8)
+        NI_TERM_BATCH(4)
+        NI_TERM_BATCH(2)
+        NI_TERM_BATCH(1)
 #undef NI_TERM_BATCH
-        }
     }
 
     // generated noise (pure ALU; overlaps loads still in flight)
@@ -124,74 +91,88 @@ __global__ void __launch_bounds__(NI_BLOCK, (PIX ? 6 : (NG >= 1 && NT >= 6) ? 8 
     if (n_gen > 0) {
         const uint64_t eoff = effective_offset(s.elem_offset, s.elem_offset_dev);
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
+        for (int g = 0; g < (NT >= 0 ? NG : NI_MAX_GEN); ++g) {
+            if (g < n_gen) {
+                float z[VEC];
+                normal_vec<VEC>(eoff + (uint64_t)v * VEC, s.gen_tid[g], s.keys, z);
+                if (s.gen_dst[g] != nullptr) {
+                    store_raw<T, VEC>(static_cast<T *>(s.gen_dst[g]) + (size_t)v * VEC, pack<T, VEC>(z));
 #pragma unroll
-            for (int g = 0; g < (NT >= 0 ? NG : NI_MAX_GEN); ++g) {
-                if (g < n_gen) {
-                    float z[VEC];
-                    normal_vec<VEC>(eoff + (uint64_t)v[i] * VEC, s.gen_tid[g], s.keys, z);
-                    if (s.gen_dst[g] != nullptr) {
-                        store_raw<T, VEC>(static_cast<T *>(s.gen_dst[g]) + (size_t)v[i] * VEC, pack<T, VEC>(z));
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) z[j] = round_to<T>(z[j]);
-                    }
-                    const float c = s.gen_c[g];
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(c, z[j], acc[i][j]);
+                    for (int j = 0; j < VEC; ++j) z[j] = round_to<T>(z[j]);
                 }
+                const float c = s.gen_c[g];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(c, z[j], acc[j]);
             }
         }
     }
 
     // x0 = a*x + b0*out0 + b1*out1, kept in the ring, enters the sum with A[k,k]; first-order rows add c_xin * x_k
+    float x0[VEC], f[VEC];
+    unpack<TO, VEC>(ro0, f);
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-        float x0[VEC], f[VEC];
-        unpack<TO, VEC>(ro0[i], f);
+    for (int j = 0; j < VEC; ++j) x0[j] = s.b0 * f[j];
+    if constexpr (M == 2) {
+        unpack<TO, VEC>(ro1, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) x0[j] = s.b0 * f[j];
-        if constexpr (M == 2) {
-            unpack<TO, VEC>(ro1[i], f);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) x0[j] = fmaf(s.b1, f[j], x0[j]);
-        }
-        if (has_x) {
-            unpack<T, VEC>(rx[i], f);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) x0[j] = fmaf(s.a, f[j], x0[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) x0[j] = round_to<T>(x0[j]);
-        if (s.x0_dst != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x0_dst) + (size_t)v[i] * VEC, pack<T, VEC>(x0));
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(s.c_x0, x0[j], acc[i][j]);
-        if (has_x && s.c_xin != 0.f) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[i][j] = fmaf(s.c_xin, f[j], acc[i][j]);
-        }
-        if (s.bias != 0.f) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) acc[i][j] += s.bias;
-        }
-        if (s.x_next != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x_next) + (size_t)v[i] * VEC, pack<T, VEC>(acc[i]));
-        if (s.x_next_lp != nullptr) {
-            if (s.lp_dtype == NI_BF16) store_raw<__nv_bfloat16, VEC>(static_cast<__nv_bfloat16 *>(s.x_next_lp) + (size_t)v[i] * VEC, pack<__nv_bfloat16, VEC>(acc[i]));
-            else store_raw<__half, VEC>(static_cast<__half *>(s.x_next_lp) + (size_t)v[i] * VEC, pack<__half, VEC>(acc[i]));
-        }
+        for (int j = 0; j < VEC; ++j) x0[j] = fmaf(s.b1, f[j], x0[j]);
     }
+    if (has_x) {
+        unpack<T, VEC>(rx, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) x0[j] = fmaf(s.a, f[j], x0[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) x0[j] = round_to<T>(x0[j]);
+    if (s.x0_dst != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x0_dst) + (size_t)v * VEC, pack<T, VEC>(x0));
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = fmaf(s.c_x0, x0[j], acc[j]);
+    if (has_x && s.c_xin != 0.f) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(s.c_xin, f[j], acc[j]);
+    }
+    if (s.bias != 0.f) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] += s.bias;
+    }
+    if (s.x_next != nullptr) store_raw<T, VEC>(static_cast<T *>(s.x_next) + (size_t)v * VEC, pack<T, VEC>(acc));
+    if (s.x_next_lp != nullptr) {
+        if (s.lp_dtype == NI_BF16) store_raw<__nv_bfloat16, VEC>(static_cast<__nv_bfloat16 *>(s.x_next_lp) + (size_t)v * VEC, pack<__nv_bfloat16, VEC>(acc));
+        else store_raw<__half, VEC>(static_cast<__half *>(s.x_next_lp) + (size_t)v * VEC, pack<__half, VEC>(acc));
+    }
+}
 
-    // fused output stage of the LAST step: NCHW float -> NHWC uint8 with the reference's truncating cast.  The thread
-    // holds 4 pixels x 3 channels = 12 consecutive output bytes; the warp's 384 bytes go out as 24 x 16 B.
+template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP>
+__global__ void __launch_bounds__(NI_BLOCK, (PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 : NI_LEAN_MIN_BLOCKS)) ni_step_lean_kernel(const __grid_constant__ LeanArgs s, const __grid_constant__ TermTable<CAP> tab)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    pdl_launch_dependents();
+
     if constexpr (PIX) {
+        // fused output stage of the LAST step: NCHW float -> NHWC uint8 with the reference's truncating cast.  Thread g owns
+        // pixels [4q, 4q+4) of sample n: it walks the three channel planes one after the other (each pass is an ordinary
+        // vector of the step), keeps 4 bytes per channel, and the warp's 384 output bytes go out as 24 x 16 B.
         __shared__ __align__(16) uint32_t stage[NI_BLOCK * 3];
+        const uint32_t g = blockIdx.x * NI_BLOCK + threadIdx.x;
+        if (g >= s.n_pix_threads) return; // host guarantees whole warps (hw_vec % 32 == 0)
+        const uint32_t sample = g / s.hw_vec;
+        const uint32_t q = g - sample * s.hw_vec;
+        pdl_wait();
         uint8_t b[12];
+        float ss = 0.f;
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t v = sample * s.vec_per_sample + c * s.hw_vec + q;
+            float acc[VEC];
+            lean_vector<T, TO, NT, NG, M, POL, CAP>(s, tab, v, v + sample * s.out_extra_vec, acc);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float y = (round_to<T>(acc[c][p]) * s.px_scale + s.px_shift) * 255.0f;
+            for (int p = 0; p < 4; ++p) {
+                const float r = round_to<T>(acc[p]);
+                const float y = (r * s.px_scale + s.px_shift) * 255.0f;
                 b[p * 3 + c] = (uint8_t)(int)fminf(fmaxf(y, 0.f), 255.f);
+                ss = fmaf(r, r, ss);
             }
+        }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint32_t *ws = stage + warp * 96;
 #pragma unroll
@@ -199,33 +180,44 @@ __global__ void __launch_bounds__(NI_BLOCK, (PIX ? 6 : (NG >= 1 && NT >= 6) ? 8 
         __syncwarp();
         if (lane < 24) {
             const uint32_t g0 = blockIdx.x * NI_BLOCK + warp * 32; // first thread of this warp
-            const uint4 q = *reinterpret_cast<const uint4 *>(ws + lane * 4);
-            st128(s.pixels + (size_t)g0 * 12 + lane * 16, q);
+            const uint4 o = *reinterpret_cast<const uint4 *>(ws + lane * 4);
+            st128(s.pixels + (size_t)g0 * 12 + lane * 16, o);
         }
-    }
+        (void)ss;
+        return;
+    } else {
+        const uint32_t v = blockIdx.x * NI_BLOCK + threadIdx.x;
+        if (v >= s.nvec) return;
+        uint32_t sample = 0;
+        if (s.out_extra_vec != 0 || s.sumsq != nullptr) {
+            if (s.tile_in_sample) sample = s.tps_mul == 0 ? blockIdx.x : (__umulhi(blockIdx.x, s.tps_mul) >> s.tps_shr);
+            else sample = v / s.vec_per_sample;
+        }
+        pdl_wait();
+        float acc[VEC];
+        lean_vector<T, TO, NT, NG, M, POL, CAP>(s, tab, v, v + sample * s.out_extra_vec, acc);
 
-    // per-sample sum of squares: warp shuffle, one atomic per warp (per lane only where a warp straddles samples)
-    if (s.sumsq != nullptr) {
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < VPT; ++i)
+        // per-sample sum of squares: warp shuffle, one atomic per warp (per lane only where a warp straddles samples)
+        if (s.sumsq != nullptr) {
+            float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const float r = round_to<T>(acc[i][j]);
+                const float r = round_to<T>(acc[j]);
                 ss = fmaf(r, r, ss);
             }
-        const unsigned mask = __activemask();
-        bool fast = mask == 0xffffffffu;
-        if (fast) {
-            const uint32_t s0 = __shfl_sync(0xffffffffu, sample, 0);
-            fast = __all_sync(0xffffffffu, sample == s0);
-        }
-        if (fast) {
+            const unsigned mask = __activemask();
+            bool fast = mask == 0xffffffffu;
+            if (fast) {
+                const uint32_t s0 = __shfl_sync(0xffffffffu, sample, 0);
+                fast = __all_sync(0xffffffffu, sample == s0);
+            }
+            if (fast) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(s.sumsq + sample, ss);
-        } else {
-            atomicAdd(s.sumsq + sample, ss);
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(s.sumsq + sample, ss);
+            } else {
+                atomicAdd(s.sumsq + sample, ss);
+            }
         }
     }
 }
@@ -323,17 +315,28 @@ int launch_step_lean(const NiStepDesc *d, const void *x_in_eff, bool stream, cud
     a.n_terms = d->n_terms; a.n_gen = d->n_gen; a.lp_dtype = d->lp_dtype; a.accumulate = d->accumulate;
 
     if (d->pixels_u8 != nullptr) {
-        // output-stage instantiation: fp32 state, 3 channels, whole warps per channel plane, <= 32 terms, no extras
+        // output-stage instantiation: fp32 state, 3 channels, whole warps per channel plane, <= 8 stored terms, no extras
         if constexpr (std::is_same<T, float>::value && std::is_same<TO, float>::value) {
             const int64_t hw_vec = d->per_sample / 3 / VEC;
-            const bool ok = d->px_channels == 3 && d->per_sample % (3 * VEC) == 0 && hw_vec % 32 == 0 && d->n_terms <= 32 && d->n_gen == 0 && !d->accumulate &&
+            const bool ok = d->px_channels == 3 && d->per_sample % (3 * VEC) == 0 && hw_vec % 32 == 0 && d->n_terms <= 8 && d->n_gen == 0 && !d->accumulate &&
                             d->sumsq == nullptr && d->x_next_lp == nullptr && aligned16(d->pixels_u8) && batch * hw_vec < (1ll << 31);
             if (!ok) return NI_OK;
             a.hw_vec = (uint32_t)hw_vec;
             a.n_pix_threads = (uint32_t)(batch * hw_vec);
             *used = true;
-            if (d->out1 != nullptr) return stream ? launch_one<float, float, -1, 0, 2, NI_STREAM_LOAD_POLICY, true, 32>(a, d, st) : launch_one<float, float, -1, 0, 2, NI_LOAD_POLICY, true, 32>(a, d, st);
-            return stream ? launch_one<float, float, -1, 0, 1, NI_STREAM_LOAD_POLICY, true, 32>(a, d, st) : launch_one<float, float, -1, 0, 1, NI_LOAD_POLICY, true, 32>(a, d, st);
+#define NI_PIX(NTV)                                                                                                                        \
+    case NTV:                                                                                                                              \
+        if (d->out1 != nullptr)                                                                                                            \
+            return stream ? launch_one<float, float, NTV, 0, 2, NI_STREAM_LOAD_POLICY, true, (NTV > 0 ? NTV : 1)>(a, d, st)                \
+                          : launch_one<float, float, NTV, 0, 2, NI_LOAD_POLICY, true, (NTV > 0 ? NTV : 1)>(a, d, st);                      \
+        return stream ? launch_one<float, float, NTV, 0, 1, NI_STREAM_LOAD_POLICY, true, (NTV > 0 ? NTV : 1)>(a, d, st)                    \
+                      : launch_one<float, float, NTV, 0, 1, NI_LOAD_POLICY, true, (NTV > 0 ? NTV : 1)>(a, d, st);
+            switch (d->n_terms) {
+                NI_PIX(0) NI_PIX(1) NI_PIX(2) NI_PIX(3) NI_PIX(4) NI_PIX(5) NI_PIX(6) NI_PIX(7)
+            default:
+                NI_PIX(8)
+            }
+#undef NI_PIX
         }
         return NI_OK;
     }

@@ -95,3 +95,23 @@ def accumulate_images(acc: FidAccumulator, images_u8_nhwc: torch.Tensor, feature
             f = f.mean(dim=(2, 3))
         acc.update(f)
     return acc
+
+
+def inception_pool3_standin(device="cuda", dtype=torch.float32):
+    """Inception-shaped feature extractor for offline runs: torchvision's InceptionV3 architecture (what pytorch_fid's
+    `InceptionV3([3])` wraps, src/CIFAR10NaturalInference.py:52-70) with RANDOM weights -- the FID checkpoint cannot be
+    downloaded here -- returning the 2048-d pool3 activations.  Input: float NCHW in [0, 1]; resized to 299x299 (bilinear)
+    and scaled to [-1, 1] like pytorch_fid's resize_input / normalize_input.  Scaffolding: it gives the evaluation flow its
+    real shapes and cost (5.7 GFLOP per image), not meaningful FID values."""
+    from torchvision.models import inception_v3
+    torch.manual_seed(0)
+    net = inception_v3(weights=None, aux_logits=False, init_weights=False)
+    net.fc = torch.nn.Identity()
+    net = net.to(device=device, dtype=dtype).eval()
+
+    @torch.no_grad()
+    def features(x):
+        x = torch.nn.functional.interpolate(x.to(dtype), size=(299, 299), mode="bilinear", align_corners=False)
+        return net(2.0 * x - 1.0).float()
+
+    return features

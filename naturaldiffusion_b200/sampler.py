@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from typing import Callable, List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 import torch
 
@@ -100,6 +102,8 @@ class NaturalInferenceSampler:
         self._launches: Optional[List[List[StepLaunch]]] = None
         self._launch_key = None
         self._launch_cache = {}
+        # NVTX ranges around sample() and each fused step (timeline tools: nsys / ncu --nvtx); off unless NI_NVTX=1
+        self.nvtx = os.environ.get("NI_NVTX", "") == "1"
         self.kernel_launches_per_trajectory = sum(p.launches(k, eps0 == "stored") for k in range(self.K))
 
     def set_sample_offset(self, sample_offset: int):
@@ -283,15 +287,27 @@ class NaturalInferenceSampler:
             st = stream_ptr(self.device)
             trace = []
             x = x_init.view(shape)
+            nvtx = torch.cuda.nvtx if self.nvtx else None
+            if nvtx:
+                nvtx.range_push(f"ni.sample K={self.K} B={self.batch}")
             for k in range(self.K):
                 x_model = x if (self._lp is None or k == 0) else self._lp[k % 2].view(shape)
+                if nvtx:
+                    nvtx.range_push(f"denoiser k={k}")
                 outs = denoiser(x_model, k)
+                if nvtx:
+                    nvtx.range_pop()
+                    nvtx.range_push(f"ni_step k={k}")
                 self.step(k, outs, st)
+                if nvtx:
+                    nvtx.range_pop()
                 x = (out if (k == self.K - 1 and out is not None) else self._X[(k + 1) % 2]).view(shape)
                 if record:
                     trace.append(dict(x0=self.x0_slot(k).clone(), x_next=x.clone()))
             if noise is None or any(L.desc.n_gen for row in self._launches for L in row):
                 self._advance_noise(st)
+            if nvtx:
+                nvtx.range_pop()
         if pixels_out is not None:
             return pixels_out
         return (x, trace) if record else x

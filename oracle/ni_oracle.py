@@ -43,9 +43,10 @@ def load_sd3_csv(path):
     Follows ``pd.read_csv(path, index_col=0).to_numpy()`` (src/SD3NaturalInference.py:196)
     without pandas so the oracle has no dependency the product does not have.
     """
-    with open(path, "r") as f:
-        rows = [ln.strip().split(",") for ln in f if ln.strip()]
-    return np.array([[float(v) for v in r[1:]] for r in rows[1:]], dtype=np.float64)
+    # numpy's own csv reader -- deliberately NOT the line-splitting parser of the product (naturaldiffusion_b200/coeffs.py),
+    # so that the checker and the thing checked do not share code for reading this table
+    table = np.genfromtxt(path, delimiter=",", skip_header=1, dtype=np.float64)
+    return np.atleast_2d(table)[:, 1:].copy()
 
 
 def sd3_sigmas(num_step=28, shift=3.0, num_train=1000):
