@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""Top stall locations (SASS) of one ni_step launch from an ncu report with --import-source on.
-usage: scripts/source_hotspots.py report.ncu-rep [launch_index] > profiles/...txt"""
+"""Top stall locations (SASS) of one ni_step launch from an ncu report with --import-source on, or from the
+`--page source --csv` export of one launch that scripts/r02_profile.sh makes on the box.
+usage: scripts/source_hotspots.py report.ncu-rep|source.csv [launch_index] > profiles/...txt"""
 import csv
 import subprocess
 import sys
 
 rep, which = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 7
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:ni_step_kernel"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    txt = open(rep).read()
+else:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:ni_step"], capture_output=True, text=True).stdout
 blocks, cur = [], None
 for r in csv.reader(txt.splitlines()):
     if r and r[0] == "Kernel Name":
         cur = []
         blocks.append(cur)
+        print("kernel:", r[1][:150])
         continue
     if cur is not None and r:
         cur.append(r)
