@@ -74,13 +74,18 @@ def run(samples=2000, batch=500, weights="step_10_weight_42.npz", feat_dim=256, 
     dt = time.perf_counter() - t0
     ar_ms = (time.perf_counter() - t_ar) * 1e3
     mu, sigma = acc.finalize()
-    rng = np.random.default_rng(0)                                     # stand-in for weights/cifar10_mu_sigma.npz
-    ref = rng.standard_normal((4 * feat_dim, feat_dim)) * 0.05 + mu
-    fid = frechet_distance(np.mean(ref, 0), np.cov(ref, rowvar=False), mu, sigma)
+    fid = float("nan")
+    if rank == 0:                                                      # the O(d^3) host step runs once, like in the reference
+        rng = np.random.default_rng(0)                                 # stand-in for weights/cifar10_mu_sigma.npz
+        ref = rng.standard_normal((4 * feat_dim, feat_dim)) * 0.05 + mu
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                            # random-init features: near-singular covariances
+            fid = frechet_distance(np.mean(ref, 0), np.cov(ref, rowvar=False), mu, sigma)
     if rank == 0 and not quiet:
         print(f"{samples} samples on {world} GPU(s) in {dt:.2f} s ({samples / dt:.0f} samples/s incl. random-init NCSN++); "
               f"features={features} ({feat_dim}-d); all-reduce of {acc.buf.numel() * 8 / 1e6:.1f} MB statistics {ar_ms:.2f} ms; "
-              f"n={int(acc.n)}; plumbing-only FID vs synthetic statistics = {fid:.4f}")
+              f"n={int(acc.n)}; plumbing-only FID vs synthetic statistics = {fid:.4f}", flush=True)
     return dict(n=acc.n, mu=mu, sigma=sigma, fid=fid, seconds=dt)
 
 

@@ -62,6 +62,23 @@ template <int POL> __device__ __forceinline__ uint4 ld128_pol(const void *p)
     else asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// 256-bit global access: Blackwell only (PTX ld/st.global.v8.b32, SASS LDG.E.ENL2.256 / STG.E.ENL2.256); 32-byte aligned
+struct Vec256 { uint32_t w[8]; };
+template <int POL> __device__ __forceinline__ Vec256 ld256_pol(const void *p)
+{
+    Vec256 r;
+    if constexpr (POL == 1)
+        asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    else
+        asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(void *p, const uint32_t (&w)[8])
+{
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
 template <int POL> __device__ __forceinline__ uint2 ld64_pol(const void *p)
 {
     uint2 r;
@@ -103,8 +120,9 @@ template <typename T, int VEC, int POL = NI_LOAD_POLICY> __device__ __forceinlin
     Raw<T, VEC> r;
     constexpr int BYTES = Raw<T, VEC>::BYTES;
     if constexpr (BYTES == 32) {
-        uint4 a = ld128_pol<POL>(p), b = ld128_pol<POL>(reinterpret_cast<const char *>(p) + 16);
-        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+        const Vec256 a = ld256_pol<POL>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.w[i] = a.w[i];
     } else if constexpr (BYTES == 16) {
         uint4 a = ld128_pol<POL>(p);
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
@@ -176,8 +194,7 @@ template <typename T, int VEC> __device__ __forceinline__ void store_raw(T *p, c
 {
     constexpr int BYTES = Raw<T, VEC>::BYTES;
     if constexpr (BYTES == 32) {
-        st128(p, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
-        st128(reinterpret_cast<char *>(p) + 16, make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]));
+        st256(p, r.w);
     } else if constexpr (BYTES == 16) {
         st128(p, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
     } else if constexpr (BYTES == 8) {

@@ -22,6 +22,10 @@ namespace {
 #ifndef NI_LEAN_MIN_BLOCKS
 #define NI_LEAN_MIN_BLOCKS 10
 #endif
+// bytes of the storage type each thread moves per tensor: 16 (LDG.E.128) or 32 (Blackwell's LDG.E.ENL2.256)
+#ifndef NI_LEAN_VEC_BYTES
+#define NI_LEAN_VEC_BYTES 16
+#endif
 
 // everything a launch needs besides the term table; 32-bit addressing
 struct LeanArgs {
@@ -49,10 +53,10 @@ struct LeanArgs {
 // One vector (VEC elements) of one step: every load issued before the first FMA, the sum in table order, generated noise,
 // the x0 stage, the stores of x0_k / x_{k+1} / the low-precision copy.  Leaves x_{k+1} (fp32, before storage rounding) in acc.
 // NT >= 0: exactly NT stored terms, NG/M exact.  NT < 0: runtime n_terms / n_gen, M still exact.
-template <typename T, typename TO, int NT, int NG, int M, int POL, int CAP>
-__device__ __forceinline__ void lean_vector(const LeanArgs &s, const TermTable<CAP> &tab, uint32_t v, uint32_t vo, float (&acc)[16 / (int)sizeof(T)])
+template <typename T, typename TO, int NT, int NG, int M, int POL, int CAP, int VB>
+__device__ __forceinline__ void lean_vector(const LeanArgs &s, const TermTable<CAP> &tab, uint32_t v, uint32_t vo, float (&acc)[VB / (int)sizeof(T)])
 {
-    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int VEC = VB / (int)sizeof(T);
     const bool has_x = s.x_in != nullptr;
     Raw<TO, VEC> ro0, ro1;
     Raw<T, VEC> rx;
@@ -145,7 +149,8 @@ __device__ __forceinline__ void lean_vector(const LeanArgs &s, const TermTable<C
 template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP>
 __global__ void __launch_bounds__(NI_BLOCK, (PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 : NI_LEAN_MIN_BLOCKS)) ni_step_lean_kernel(const __grid_constant__ LeanArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
-    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int VB = PIX ? 16 : NI_LEAN_VEC_BYTES;
+    constexpr int VEC = VB / (int)sizeof(T);
     pdl_launch_dependents();
 
     if constexpr (PIX) {
@@ -164,7 +169,7 @@ __global__ void __launch_bounds__(NI_BLOCK, (PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 
         for (int c = 0; c < 3; ++c) {
             const uint32_t v = sample * s.vec_per_sample + c * s.hw_vec + q;
             float acc[VEC];
-            lean_vector<T, TO, NT, NG, M, POL, CAP>(s, tab, v, v + sample * s.out_extra_vec, acc);
+            lean_vector<T, TO, NT, NG, M, POL, CAP, VB>(s, tab, v, v + sample * s.out_extra_vec, acc);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const float r = round_to<T>(acc[p]);
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(NI_BLOCK, (PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 
         }
         pdl_wait();
         float acc[VEC];
-        lean_vector<T, TO, NT, NG, M, POL, CAP>(s, tab, v, v + sample * s.out_extra_vec, acc);
+        lean_vector<T, TO, NT, NG, M, POL, CAP, VB>(s, tab, v, v + sample * s.out_extra_vec, acc);
 
         // per-sample sum of squares: warp shuffle, one atomic per warp (per lane only where a warp straddles samples)
         if (s.sumsq != nullptr) {
@@ -291,9 +296,20 @@ int launch_nt(const LeanArgs &a, const NiStepDesc *d, bool stream, cudaStream_t 
 template <typename T, typename TO>
 int launch_step_lean(const NiStepDesc *d, const void *x_in_eff, bool stream, cudaStream_t st, bool *used)
 {
-    constexpr int VEC = 16 / (int)sizeof(T);
+    const bool pix = d->pixels_u8 != nullptr;
+    const int VEC = (pix ? 16 : NI_LEAN_VEC_BYTES) / (int)sizeof(T);
     *used = false;
     if (!d->has_x0 || d->out0 == nullptr) return NI_OK;
+    if (!pix && NI_LEAN_VEC_BYTES == 32) {
+        // 256-bit accesses need 32-byte alignment and whole 32-byte vectors everywhere (ni_step checked the 16-byte conditions)
+        auto al = [](const void *p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+        const uintptr_t ob = (uintptr_t)(VEC * (int)sizeof(TO));
+        bool ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && d->out_sample_stride % VEC == 0 && al(x_in_eff, 32) && al(d->out0, ob) && al(d->out1, ob) &&
+                  al(d->x0_dst, 32) && al(d->x_next, 32) && al(d->x_next_lp, (uintptr_t)VEC * 2);
+        for (int i = 0; i < d->n_terms && ok; ++i) ok = al(d->term_ptrs_host[i], 32);
+        for (int g = 0; g < d->n_gen && ok; ++g) ok = al(d->gen_dst[g], 32);
+        if (!ok) return NI_OK;
+    }
     const int64_t nvec = d->numel / VEC;
     const int64_t batch = d->numel / d->per_sample;
     const int64_t out_vec_total = batch * (d->out_sample_stride / VEC);
