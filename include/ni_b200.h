@@ -113,13 +113,15 @@ int ni_version(void);
 const char *ni_last_error(void);
 /* kernels launched by this library in this process so far (bench.py's `gpu_launches`) */
 int64_t ni_launch_count(void);
-/* how many of those were ni_step launches served by the row-shape-specialised kernels (ni_step_lean.cu) */
+/* how many of those were ni_step launches served by the row-shape-specialised kernels (ni_step_lean.cuh) */
 int64_t ni_lean_launch_count(void);
 
 /* Tuning knobs, process-wide: "variant" 0 auto (row-shape-specialised kernels, generic kernel for what they do not cover)
  * | 1 generic direct-load kernel | 2 TMA-staged kernel when eligible;
  * "tma_max_stages" 2..32; "tma_warps" 1..16; "tma_smem_kb" 16..226; "tma_ctas_per_sm" 1..4; "pdl" 0|1 (programmatic
- * dependent launch of the direct-load step kernel, default 1); "load_policy" 0 auto | 1 L2-friendly loads
+ * dependent launch of the direct-load step kernel, default 1); "wide" 0|1 (fp32 state: the 256-bit LDG.E.ENL2.256 / STG.E.ENL2.256
+ * instantiations of the specialised step kernels whenever every pointer is 32-byte aligned, default 1); "tma_tile_kb" 2|4,
+ * "tma_l2_hint" 0..3, "tma_dynamic" 0|1 (TMA variant); "load_policy" 0 auto | 1 L2-friendly loads
  * (ld.global.L1::no_allocate) | 2 streaming loads (plain ld.global) -- auto picks L2-friendly loads when what the
  * launch writes fits in 0.6 of the L2 and is >= 1/16 of its traffic, streaming otherwise (measured:
  * profiles/r01_policy_sweep.txt).  Results do not depend on them. */

@@ -12,10 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SRCS = [os.path.join(CSRC, n) for n in ("ni_kernels.cu", "ni_step_lean.cu", "ni_fid.cu")]
+SRCS = [os.path.join(CSRC, n) for n in ("ni_kernels.cu", "ni_step_lean_f32.cu", "ni_step_lean_f16.cu", "ni_step_lean_bf16.cu", "ni_fid.cu")]
 SRC = SRCS[0]
 HDR = os.path.join(ROOT, "include", "ni_b200.h")
-DEPS = SRCS + [HDR, os.path.join(CSRC, "ni_common.cuh")]
+DEPS = SRCS + [HDR, os.path.join(CSRC, "ni_common.cuh"), os.path.join(CSRC, "ni_step_lean.cuh")]
 OUT = os.path.join(HERE, "libni_b200.so")
 
 NVCC_FLAGS = [

@@ -46,6 +46,7 @@ namespace ni {
 int fail(int code, const char *fmt, ...);
 int check_launch(const char *what);
 int opt_pdl();
+int opt_wide();
 void count_lean_launch();
 struct DevInfo { int sms; int64_t l2_bytes; };
 const DevInfo &dev_info();
@@ -369,7 +370,7 @@ inline void launch_pdl(Kern kern, unsigned blocks, unsigned threads, size_t smem
     cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
-// ni_step_lean.cu: the specialised step kernels.  *used = false when the launch is not eligible (generic kernel takes it).
+// ni_step_lean.cuh: the specialised step kernels.  *used = false when the launch is not eligible (generic kernel takes it).
 template <typename T, typename TO>
 int launch_step_lean(const NiStepDesc *d, const void *x_in_eff, bool stream, cudaStream_t st, bool *used);
 

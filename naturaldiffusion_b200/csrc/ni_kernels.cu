@@ -42,6 +42,7 @@ std::atomic<int> g_tma_ctas_per_sm{2};
 std::atomic<int> g_tma_tile_kb{2};   // bytes per source per stage: 2 or 4 KB
 std::atomic<int> g_tma_l2_hint{0};   // cp.async.bulk L2 cache hint: 0 none, 1 evict_first, 2 evict_last, 3 evict_normal
 std::atomic<int> g_tma_dynamic{0};   // 1: tiles claimed from a global counter instead of blockIdx.x + q * gridDim.x
+std::atomic<int> g_wide{1};          // fp32 state: 256-bit (LDG.E.ENL2.256) instantiations of the specialised step kernels when eligible
 std::atomic<int> g_pdl{1};           // programmatic dependent launch for the direct-load step kernels
 std::atomic<int> g_load_policy{0};   // step-kernel load flavour: 0 by launch footprint vs L2, 1 always L2-friendly (NA), 2 always streaming
 } // namespace
@@ -64,6 +65,7 @@ int check_launch(const char *what)
 }
 
 int opt_pdl() { return g_pdl.load(std::memory_order_relaxed); }
+int opt_wide() { return g_wide.load(std::memory_order_relaxed); }
 void count_lean_launch() { g_lean_launches.fetch_add(1, std::memory_order_relaxed); }
 
 const DevInfo &dev_info()
@@ -701,7 +703,7 @@ template <typename T, typename TO> int launch_step(StepArgs &a, const NiStepDesc
         }
     }
     if (vec_ok) {
-        if (g_variant.load() == 0) { // the specialised kernels (ni_step_lean.cu) take every launch they are built for
+        if (g_variant.load() == 0) { // the specialised kernels (ni_step_lean.cuh) take every launch they are built for
             bool used = false;
             const int rc = launch_step_lean<T, TO>(d, a.x_in, launch_streams(d), st, &used);
             if (rc != NI_OK || used) return rc;
@@ -733,6 +735,7 @@ int ni_set_option(const char *name, int value)
     if (!strcmp(name, "tma_warps")) { if (value < 1 || value > TMA_MAX_WARPS) return fail(NI_ERR_INVALID, "tma_warps must be 1..%d", TMA_MAX_WARPS); g_tma_warps = value; return NI_OK; }
     if (!strcmp(name, "tma_smem_kb")) { if (value < 16 || value > 226) return fail(NI_ERR_INVALID, "tma_smem_kb must be 16..226"); g_tma_smem_kb = value; return NI_OK; }
     if (!strcmp(name, "pdl")) { g_pdl = value ? 1 : 0; return NI_OK; }
+    if (!strcmp(name, "wide")) { g_wide = value ? 1 : 0; return NI_OK; }
     if (!strcmp(name, "load_policy")) { if (value < 0 || value > 2) return fail(NI_ERR_INVALID, "load_policy must be 0..2"); g_load_policy = value; return NI_OK; }
     if (!strcmp(name, "tma_tile_kb")) { if (value != 2 && value != 4) return fail(NI_ERR_INVALID, "tma_tile_kb must be 2 or 4"); g_tma_tile_kb = value; return NI_OK; }
     if (!strcmp(name, "tma_l2_hint")) { if (value < 0 || value > 3) return fail(NI_ERR_INVALID, "tma_l2_hint must be 0..3"); g_tma_l2_hint = value; return NI_OK; }

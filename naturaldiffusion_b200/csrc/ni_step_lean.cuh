@@ -1,4 +1,4 @@
-// ni_step_lean.cu -- the production instantiations of the fused Natural Inference step (ni_step, include/ni_b200.h).
+// ni_step_lean.cuh -- the production instantiations of the fused Natural Inference step (ni_step, include/ni_b200.h).
 //
 // Same arithmetic, same accumulation order and therefore the same bits as the generic kernel in ni_kernels.cu
 // (tests/test_gpu_parity.py::test_lean_kernel_is_bit_identical_to_generic), with the per-thread overhead removed.  The
@@ -14,6 +14,7 @@
 //   * the fused uint8 output stage (last step) has its own instantiation in which a thread owns the C = 3 channel
 //     planes of 4 consecutive pixels, the warp stages its 384 bytes in shared memory and stores them as 24 x 16 B.
 // Still an HBM-streaming kernel: no tensor cores, one 128-bit load per tensor per thread, all issued before the first FMA.
+#pragma once
 #include "ni_common.cuh"
 
 namespace ni {
@@ -22,9 +23,16 @@ namespace {
 #ifndef NI_LEAN_MIN_BLOCKS
 #define NI_LEAN_MIN_BLOCKS 10
 #endif
-// bytes of the storage type each thread moves per tensor: 16 (LDG.E.128) or 32 (Blackwell's LDG.E.ENL2.256)
-#ifndef NI_LEAN_VEC_BYTES
-#define NI_LEAN_VEC_BYTES 16
+// Bytes of the storage type each thread moves per tensor: 16 (LDG.E.128) or 32 (Blackwell's 256-bit global access,
+// PTX ld/st.global.v8.b32 -> SASS LDG.E.ENL2.256 / STG.E.ENL2.256).  Measured on B200 (profiles/r02_vec256.jsonl): with
+// fp32 state the 32-byte kernels win everywhere -- half the threads, half the per-thread overhead per byte: C2 +0.7 %,
+// C3 +0.4 %, C4 dense +0.6 %, and +34 % on the DDPM-250 first-order step whose cost is the in-kernel noise generator --
+// with fp16 state (16 elements per thread) they gain 1.3-2.3 % on the launches that stream far more than the L2 holds (SD3 dense
+// rows, B 256) and lose 4-12 % on the L2-resident ones (SD3 first-order / sharp at B 64: 33 MB tensors).  So: fp32 state takes
+// the 256-bit instantiation whenever everything is 32-byte aligned, 16-bit state only for launches that get the streaming load
+// flavour (launch_streams()).  NI_LEAN_WIDE=0 builds without the 256-bit kernels.
+#ifndef NI_LEAN_WIDE
+#define NI_LEAN_WIDE 1
 #endif
 
 // everything a launch needs besides the term table; 32-bit addressing
@@ -146,10 +154,10 @@ __device__ __forceinline__ void lean_vector(const LeanArgs &s, const TermTable<C
     }
 }
 
-template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP>
-__global__ void __launch_bounds__(NI_BLOCK, (PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 : NI_LEAN_MIN_BLOCKS)) ni_step_lean_kernel(const __grid_constant__ LeanArgs s, const __grid_constant__ TermTable<CAP> tab)
+template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP, int VB>
+__global__ void __launch_bounds__(NI_BLOCK, (VB == 32 ? 6 : PIX ? 8 : (NG >= 1 && NT >= 6) ? 8 : NI_LEAN_MIN_BLOCKS)) ni_step_lean_kernel(const __grid_constant__ LeanArgs s, const __grid_constant__ TermTable<CAP> tab)
 {
-    constexpr int VB = PIX ? 16 : NI_LEAN_VEC_BYTES;
+    static_assert(!(PIX && VB != 16), "the output-stage instantiation works on 4-pixel groups");
     constexpr int VEC = VB / (int)sizeof(T);
     pdl_launch_dependents();
 
@@ -240,53 +248,53 @@ void fast_divisor(uint32_t d, uint32_t *mul, uint32_t *shr)
     *shr = (uint32_t)(p - 32);
 }
 
-template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP>
+template <typename T, typename TO, int NT, int NG, int M, int POL, bool PIX, int CAP, int VB = 16>
 int launch_one(const LeanArgs &a, const NiStepDesc *d, cudaStream_t st)
 {
     TermTable<CAP> tab;
     memset(&tab, 0, sizeof(tab));
     for (int i = 0; i < d->n_terms; ++i) { tab.ptr[i] = d->term_ptrs_host[i]; tab.c[i] = d->term_coeffs_host[i]; }
     const uint32_t work = PIX ? a.n_pix_threads : a.nvec;
-    launch_pdl(ni_step_lean_kernel<T, TO, NT, NG, M, POL, PIX, CAP>, (work + NI_BLOCK - 1) / NI_BLOCK, NI_BLOCK, 0, st, opt_pdl() != 0, a, tab);
+    launch_pdl(ni_step_lean_kernel<T, TO, NT, NG, M, POL, PIX, CAP, VB>, (work + NI_BLOCK - 1) / NI_BLOCK, NI_BLOCK, 0, st, opt_pdl() != 0, a, tab);
     count_lean_launch();
     return check_launch("ni_step (lean) launch");
 }
 
-template <typename T, typename TO, int NT, int NG, int M, int CAP>
+template <typename T, typename TO, int NT, int NG, int M, int CAP, int VB>
 int launch_pol(const LeanArgs &a, const NiStepDesc *d, bool stream, cudaStream_t st)
 {
-    if (stream) return launch_one<T, TO, NT, NG, M, NI_STREAM_LOAD_POLICY, false, CAP>(a, d, st);
-    return launch_one<T, TO, NT, NG, M, NI_LOAD_POLICY, false, CAP>(a, d, st);
+    if (stream) return launch_one<T, TO, NT, NG, M, NI_STREAM_LOAD_POLICY, false, CAP, VB>(a, d, st);
+    return launch_one<T, TO, NT, NG, M, NI_LOAD_POLICY, false, CAP, VB>(a, d, st);
 }
 
-template <typename T, typename TO, int NT, int M>
+template <typename T, typename TO, int NT, int M, int VB>
 int launch_ng(const LeanArgs &a, const NiStepDesc *d, bool stream, cudaStream_t st)
 {
-    if (d->n_gen == 0) return launch_pol<T, TO, NT, 0, M, (NT > 0 ? NT : 1)>(a, d, stream, st);
-    return launch_pol<T, TO, NT, 1, M, (NT > 0 ? NT : 1)>(a, d, stream, st);
+    if (d->n_gen == 0) return launch_pol<T, TO, NT, 0, M, (NT > 0 ? NT : 1), VB>(a, d, stream, st);
+    return launch_pol<T, TO, NT, 1, M, (NT > 0 ? NT : 1), VB>(a, d, stream, st);
 }
 
-template <typename T, typename TO, int M>
+template <typename T, typename TO, int M, int VB>
 int launch_nt(const LeanArgs &a, const NiStepDesc *d, bool stream, cudaStream_t st)
 {
     const bool exact = d->n_terms <= 8 && d->n_gen <= 1 && !d->accumulate;
     if constexpr (std::is_same<T, TO>::value) { // mixed storage/output dtypes: runtime-loop instantiation only
         if (exact) {
             switch (d->n_terms) {
-            case 0: return launch_ng<T, TO, 0, M>(a, d, stream, st);
-            case 1: return launch_ng<T, TO, 1, M>(a, d, stream, st);
-            case 2: return launch_ng<T, TO, 2, M>(a, d, stream, st);
-            case 3: return launch_ng<T, TO, 3, M>(a, d, stream, st);
-            case 4: return launch_ng<T, TO, 4, M>(a, d, stream, st);
-            case 5: return launch_ng<T, TO, 5, M>(a, d, stream, st);
-            case 6: return launch_ng<T, TO, 6, M>(a, d, stream, st);
-            case 7: return launch_ng<T, TO, 7, M>(a, d, stream, st);
-            default: return launch_ng<T, TO, 8, M>(a, d, stream, st);
+            case 0: return launch_ng<T, TO, 0, M, VB>(a, d, stream, st);
+            case 1: return launch_ng<T, TO, 1, M, VB>(a, d, stream, st);
+            case 2: return launch_ng<T, TO, 2, M, VB>(a, d, stream, st);
+            case 3: return launch_ng<T, TO, 3, M, VB>(a, d, stream, st);
+            case 4: return launch_ng<T, TO, 4, M, VB>(a, d, stream, st);
+            case 5: return launch_ng<T, TO, 5, M, VB>(a, d, stream, st);
+            case 6: return launch_ng<T, TO, 6, M, VB>(a, d, stream, st);
+            case 7: return launch_ng<T, TO, 7, M, VB>(a, d, stream, st);
+            default: return launch_ng<T, TO, 8, M, VB>(a, d, stream, st);
             }
         }
     }
-    if (d->n_terms <= 32) return launch_pol<T, TO, -1, 0, M, 32>(a, d, stream, st);
-    return launch_pol<T, TO, -1, 0, M, NI_MAX_TERMS>(a, d, stream, st);
+    if (d->n_terms <= 32) return launch_pol<T, TO, -1, 0, M, 32, VB>(a, d, stream, st);
+    return launch_pol<T, TO, -1, 0, M, NI_MAX_TERMS, VB>(a, d, stream, st);
 }
 
 } // namespace
@@ -297,19 +305,19 @@ template <typename T, typename TO>
 int launch_step_lean(const NiStepDesc *d, const void *x_in_eff, bool stream, cudaStream_t st, bool *used)
 {
     const bool pix = d->pixels_u8 != nullptr;
-    const int VEC = (pix ? 16 : NI_LEAN_VEC_BYTES) / (int)sizeof(T);
     *used = false;
     if (!d->has_x0 || d->out0 == nullptr) return NI_OK;
-    if (!pix && NI_LEAN_VEC_BYTES == 32) {
-        // 256-bit accesses need 32-byte alignment and whole 32-byte vectors everywhere (ni_step checked the 16-byte conditions)
-        auto al = [](const void *p, uintptr_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
-        const uintptr_t ob = (uintptr_t)(VEC * (int)sizeof(TO));
-        bool ok = d->numel % VEC == 0 && d->per_sample % VEC == 0 && d->out_sample_stride % VEC == 0 && al(x_in_eff, 32) && al(d->out0, ob) && al(d->out1, ob) &&
-                  al(d->x0_dst, 32) && al(d->x_next, 32) && al(d->x_next_lp, (uintptr_t)VEC * 2);
-        for (int i = 0; i < d->n_terms && ok; ++i) ok = al(d->term_ptrs_host[i], 32);
-        for (int g = 0; g < d->n_gen && ok; ++g) ok = al(d->gen_dst[g], 32);
-        if (!ok) return NI_OK;
+    // 256-bit accesses: 32-byte alignment and whole 32-byte vectors everywhere (ni_step checked the 16-byte conditions)
+    bool wide = false;
+    if constexpr (NI_LEAN_WIDE && std::is_same<T, TO>::value) {
+        auto al = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+        constexpr int V32 = 32 / (int)sizeof(T);
+        wide = !pix && opt_wide() != 0 && (sizeof(T) == 4 || stream) && d->numel % V32 == 0 && d->per_sample % V32 == 0 && d->out_sample_stride % V32 == 0 &&
+               al(x_in_eff) && al(d->out0) && al(d->out1) && al(d->x0_dst) && al(d->x_next) && al(d->x_next_lp);
+        for (int i = 0; i < d->n_terms && wide; ++i) wide = al(d->term_ptrs_host[i]);
+        for (int g = 0; g < d->n_gen && wide; ++g) wide = al(d->gen_dst[g]);
     }
+    const int VEC = (wide ? 32 : 16) / (int)sizeof(T);
     const int64_t nvec = d->numel / VEC;
     const int64_t batch = d->numel / d->per_sample;
     const int64_t out_vec_total = batch * (d->out_sample_stride / VEC);
@@ -357,14 +365,11 @@ int launch_step_lean(const NiStepDesc *d, const void *x_in_eff, bool stream, cud
         return NI_OK;
     }
     *used = true;
-    if (d->out1 != nullptr) return launch_nt<T, TO, 2>(a, d, stream, st);
-    return launch_nt<T, TO, 1>(a, d, stream, st);
+    if constexpr (NI_LEAN_WIDE && std::is_same<T, TO>::value) {
+        if (wide) return d->out1 != nullptr ? launch_nt<T, TO, 2, 32>(a, d, stream, st) : launch_nt<T, TO, 1, 32>(a, d, stream, st);
+    }
+    if (d->out1 != nullptr) return launch_nt<T, TO, 2, 16>(a, d, stream, st);
+    return launch_nt<T, TO, 1, 16>(a, d, stream, st);
 }
-
-template int launch_step_lean<float, float>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
-template int launch_step_lean<float, __half>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
-template int launch_step_lean<float, __nv_bfloat16>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
-template int launch_step_lean<__half, __half>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
-template int launch_step_lean<__nv_bfloat16, __nv_bfloat16>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
 
 } // namespace ni

@@ -1,0 +1,7 @@
+// ni_step_lean_f16.cu -- explicit instantiations of the specialised step kernels (ni_step_lean.cuh) for fp16 state; one translation unit per
+// storage type so that nvcc compiles them in parallel.
+#include "ni_step_lean.cuh"
+
+namespace ni {
+template int launch_step_lean<__half, __half>(const NiStepDesc *, const void *, bool, cudaStream_t, bool *);
+} // namespace ni

@@ -13,8 +13,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "naturaldiffusion_b200", "libni_b200.so")
-DEFAULT = [r"ni_step_lean_kernel<float, float, 4, 0, 1, 0, false", r"ni_step_lean_kernel<float, float, 0, 1, 2, 1, false",
-           r"ni_step_lean_kernel<float, float, -1, 0, 1, 0, false, 32", r"ni_step_lean_kernel<__half, __half, 1, 0, 2, 1, false",
+DEFAULT = [r"ni_step_lean_kernel<float, float, 4, 0, 1, 0, false, 4, 32>", r"ni_step_lean_kernel<float, float, 4, 0, 1, 0, false, 4, 16>",
+           r"ni_step_lean_kernel<float, float, 0, 1, 2, 1, false, 1, 32>", r"ni_step_lean_kernel<float, float, -1, 0, 1, 0, false, 32, 32>",
+           r"ni_step_lean_kernel<__half, __half, 1, 0, 2, 1, false, 1, 16>", r"ni_step_lean_kernel<__half, __half, -1, 0, 2, 0, false, 32, 32>",
            r"ni_step_lean_kernel<float, float, 3, 0, 1, 0, true", r"ni_step_kernel<float, float, 4, 32, true>",
            r"ni_step_tma_kernel<float, 2048>", r"ni_step_tma_kernel<float, 4096>", r"ni_wsum_kernel<float, float, 4, 32, 0>",
            r"ni_wsum_kernel<double, float, 2, 32, 0>", r"ni_normal_kernel<float, 4>", r"ni_fid_syrk_kernel", r"ni_pixel_kernel<float>"]
@@ -34,7 +35,8 @@ def main():
                 continue
             ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", f)
             ops = [o for o in ops if o not in ("NOP",)]
-            base = collections.Counter(re.sub(r"^(LDG\.E(?:\.NA)?(?:\.\d+)?|STG\.E(?:\.\d+)?|LDS(?:\.\d+)?|MUFU\.\w+|IMAD\.WIDE(?:\.U32)?|DMMA\.\d+|UBLKCP\.\w+\.\w+|SYNCS\.\w+(?:\.\w+)?|RED\.\w+|REDG\.\w+)?.*", lambda m: m.group(1) or m.group(0).split(".")[0], o) for o in ops)
+            ops = [re.sub(r"(LDG|STG)\.E((?:\.NA)?)\.ENL2\.256", r"\1.E\2.ENL2.256", o) for o in ops]
+            base = collections.Counter(re.sub(r"^(LDG\.E(?:\.NA)?(?:\.ENL2)?(?:\.\d+)?|STG\.E(?:\.ENL2)?(?:\.\d+)?|LDS(?:\.\d+)?|MUFU\.\w+|IMAD\.WIDE(?:\.U32)?|DMMA\.\d+|UBLKCP\.\w+\.\w+|SYNCS\.\w+(?:\.\w+)?|RED\.\w+|REDG\.\w+)?.*", lambda m: m.group(1) or m.group(0).split(".")[0], o) for o in ops)
             print(f"## {re.sub(r'[(].*', '', d)}\n   static instructions: {len(ops)}")
             print("   " + ", ".join(f"{k} {v}" for k, v in base.most_common(28)))
             full = collections.Counter(ops)

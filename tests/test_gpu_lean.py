@@ -1,4 +1,4 @@
-"""GPU tests of the row-shape-specialised step kernels (csrc/ni_step_lean.cu, round 2): bit-identical to the generic
+"""GPU tests of the row-shape-specialised step kernels (csrc/ni_step_lean.cuh, round 2): bit-identical to the generic
 kernel on every shape class they serve, the in-kernel normal transform against the fp64 oracle at its edges, and the
 BASELINE shapes that round 1 never compared with the oracle at full size (C3 batch 16384, C5 16x128x128 latents)."""
 import os
@@ -30,7 +30,7 @@ def rel_err(got, ref):
                                     (torch.float32, torch.float16)])
 @pytest.mark.parametrize("n_terms", [0, 1, 3, 5, 8, 9, 20])
 @pytest.mark.parametrize("n_gen,ncond,shape,cout", [(0, 1, (5, 4, 32, 32), 4), (1, 2, (3, 4, 32, 32), 8), (2, 2, (7, 3, 8, 8), 3),
-                                                    (1, 1, (2, 16, 32, 32), 16), (0, 2, (6, 3, 32, 32), 6)])
+                                                    (1, 1, (2, 16, 32, 32), 16), (0, 2, (6, 3, 32, 32), 6), (1, 1, (3, 1, 2, 6), 1)])
 def test_lean_kernel_is_bit_identical_to_generic(dt, odt, n_terms, n_gen, ncond, shape, cout):
     """variant 0 (specialised kernels) vs variant 1 (generic kernel): same bits for x_next, x0, kept noise and the
     low-precision copy; per-sample norms to fp32 reduction order.  Shapes cover CTA-inside-sample (multiply-shift sample
@@ -48,18 +48,23 @@ def test_lean_kernel_is_bit_identical_to_generic(dt, odt, n_terms, n_gen, ncond,
         _lib.set_option("variant", 1)
         ref = fused_step(**kw)
         _lib.set_option("variant", 0)
-        n0 = _lib.lean_launch_count()
-        got = fused_step(**kw)
-        assert _lib.lean_launch_count() == n0 + 1, "the specialised kernel did not take this launch"
+        gots = []
+        for wide in (1, 0):  # fp32 state: the 256-bit (LDG.E.ENL2.256) and the 128-bit instantiations
+            _lib.set_option("wide", wide)
+            n0 = _lib.lean_launch_count()
+            gots.append(fused_step(**kw))
+            assert _lib.lean_launch_count() == n0 + 1, "the specialised kernel did not take this launch"
     finally:
         _lib.set_option("variant", 0)
-    for key in ("x_next", "x0"):
-        assert torch.equal(got[key], ref[key]), key
-    if n_gen:
-        assert torch.equal(got["gen"][0], ref["gen"][0])
-    if kw["lp_dtype"] is not None:
-        assert torch.equal(got["x_next_lp"], ref["x_next_lp"])
-    assert torch.allclose(got["sumsq"], ref["sumsq"], rtol=1e-5)
+        _lib.set_option("wide", 1)
+    for got in gots:
+        for key in ("x_next", "x0"):
+            assert torch.equal(got[key], ref[key]), key
+        if n_gen:
+            assert torch.equal(got["gen"][0], ref["gen"][0])
+        if kw["lp_dtype"] is not None:
+            assert torch.equal(got["x_next_lp"], ref["x_next_lp"])
+        assert torch.allclose(got["sumsq"], ref["sumsq"], rtol=1e-5)
 
 
 def test_lean_pixel_stage_is_byte_identical(weights_dir):
