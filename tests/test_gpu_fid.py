@@ -59,3 +59,19 @@ def test_image_to_statistics_flow():
     ref = feat(imgs.float().div(255).permute(0, 3, 1, 2)).double().cpu().numpy()
     mu, sigma = acc.finalize()
     assert acc.n == 300 and np.allclose(mu, ref.mean(0), rtol=1e-9) and np.allclose(sigma, np.cov(ref, rowvar=False), rtol=1e-7, atol=1e-12)
+
+
+def test_fid_accumulate_rejects_bad_arguments():
+    import naturaldiffusion_b200 as ni
+    from naturaldiffusion_b200 import _lib
+    L = _lib.lib()
+    x = torch.randn(16, 64, device=DEV)
+    buf = torch.zeros(1 + 64 + 64 * 64, dtype=torch.float64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.ni_fid_accumulate(x.data_ptr(), 16, 64, 32, buf.data_ptr(), st) == -1       # ld < d
+    assert L.ni_fid_accumulate(x.data_ptr(), 16, 62, 64, buf.data_ptr(), st) == -1       # d not a multiple of 4
+    assert L.ni_fid_accumulate(x.data_ptr() + 4, 16, 64, 64, buf.data_ptr(), st) == -1   # misaligned activations
+    assert L.ni_fid_accumulate(None, 16, 64, 64, buf.data_ptr(), st) == -1 and b"ni_fid_accumulate" in L.ni_last_error()
+    assert L.ni_fid_accumulate(x.data_ptr(), 0, 64, 64, buf.data_ptr(), st) == 0 and float(buf.abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        FidAccumulator(dim=64, device=DEV).update(torch.randn(4, 32, device=DEV))

@@ -480,3 +480,22 @@ def test_kxk_epsilon_matrix_uses_column_zero_only():
     assert w and "column 0" in str(w[0].message)
     assert t.B.shape == (K, K + 1) and np.all(t.B[:, 0] == 0.5) and np.all(t.B[:, 1:] == 0)
     assert all(s.fresh is None for s in build_plan(t).steps)
+
+
+def test_bind_rank_cpus_gives_disjoint_slices(monkeypatch):
+    """8 ranks whose GPUs hang off the same NUMA node (this pool's VMs) share its CPUs out in disjoint, equal slices; ranks on
+    different nodes keep their own node"""
+    from naturaldiffusion_b200 import hostutil
+    bound = {}
+    monkeypatch.setattr(hostutil.os, "sched_setaffinity", lambda pid, cpus: bound.__setitem__("cpus", set(cpus)))
+    monkeypatch.setattr(hostutil, "gpu_local_cpus", lambda i: set(range(32)))
+    slices = []
+    for r in range(8):
+        assert hostutil.bind_rank_cpus(r, 8) == 4
+        slices.append(bound["cpus"])
+    assert set().union(*slices) == set(range(32)) and sum(len(x) for x in slices) == 32
+    monkeypatch.setattr(hostutil, "gpu_local_cpus", lambda i: set(range(16)) if i < 4 else set(range(16, 32)))
+    assert hostutil.bind_rank_cpus(5, 8) == 4 and bound["cpus"] == {20, 21, 22, 23}
+    assert hostutil.bind_rank_cpus(0, 1) == 16
+    monkeypatch.setattr(hostutil, "gpu_local_cpus", lambda i: None)
+    assert hostutil.bind_rank_cpus(0, 8) is None
