@@ -242,10 +242,12 @@ def measured_peak():
 
 
 def kernel_source_sha():
+    """hash of the sources of the dominant kernel (the specialised step kernels and the shared device helpers)"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "naturaldiffusion_b200", "csrc")
     for n in sorted(os.listdir(d)):
-        h.update(open(os.path.join(d, n), "rb").read())
+        if n.startswith("ni_step_lean") or n == "ni_common.cuh":
+            h.update(open(os.path.join(d, n), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -370,7 +370,9 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
             __syncwarp();
             if (done) {
                 // tell one consumer warp that the tiles are gone; every consumer warp needs its own notice
-                if (lane == 0) { stage_tile[st] = -1; mbar_arrive(&full[st]); }
+                // (arrive.expect_tx with 0 bytes: the same release/arrive primitive as the data path -- compute-sanitizer's racecheck
+                // does not model a plain mbarrier.arrive as ordering the stage_tile write, profiles/r02_sanitizer_racecheck.txt)
+                if (lane == 0) { stage_tile[st] = -1; mbar_expect_tx(&full[st], 0); }
                 if (++sentinels == nw) break;
             } else {
                 const int64_t e0 = tile * TILE_ELEMS;
