@@ -370,9 +370,14 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
             __syncwarp();
             if (done) {
                 // tell one consumer warp that the tiles are gone; every consumer warp needs its own notice
-                // (arrive.expect_tx with 0 bytes: the same release/arrive primitive as the data path -- compute-sanitizer's racecheck
-                // does not model a plain mbarrier.arrive as ordering the stage_tile write, profiles/r02_sanitizer_racecheck.txt)
-                if (lane == 0) { stage_tile[st] = -1; mbar_expect_tx(&full[st], 0); }
+                // The notice travels exactly like a tile -- claimed index (-1) in stage_tile, arrive.expect_tx, a 16-byte bulk copy whose
+                // completion flips the phase -- so there is ONE hand-off protocol.  (compute-sanitizer racecheck: 0 hazards,
+                // profiles/r02_sanitizer_racecheck.txt; what it did find in the first version was the consumer side, see below.)
+                if (lane == 0) {
+                    stage_tile[st] = -1;
+                    mbar_expect_tx(&full[st], 16);
+                    bulk_g2s(tiles + (size_t)st * n_src * TILE_BYTES, gbase, 16, &full[st], 0);
+                }
                 if (++sentinels == nw) break;
             } else {
                 const int64_t e0 = tile * TILE_ELEMS;
@@ -402,7 +407,12 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
             const int st = (int)(it % stages);
             const uint32_t ph = (uint32_t)((it / stages) & 1);
             mbar_wait(&full[st], ph);
-            const int64_t tile = stage_tile[st];
+            // Lane 0 alone reads the claimed index and broadcasts it: its own arrive on empty[st] below then orders that read before
+            // the producer's next write to the slot by program order.  (With all 32 lanes reading it, racecheck reported a WAR hazard
+            // between lane 31's read and the producer's next write -- ordered only through __syncwarp + lane 0's arrive.)
+            int tile32 = 0;
+            if (lane == 0) tile32 = stage_tile[st];
+            const int64_t tile = __shfl_sync(0xffffffffu, tile32, 0);
             if (tile < 0) break;
             const int64_t e_tile = tile * TILE_ELEMS;
             const unsigned char *sp = tiles + (size_t)st * n_src * TILE_BYTES + lane * 16;
