@@ -330,7 +330,7 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
     if (tid == 0) {
         for (int st = 0; st < stages; ++st) {
             mbar_init(&full[st], 1);
-            mbar_init(&empty[st], 1);
+            mbar_init(&empty[st], 32); // every lane of the consuming warp arrives: each lane's reads are ordered by its own release
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
             }
             const bool done = tile >= ntiles;
             if (done && !dynamic) break;
-            if (lane == 0) mbar_wait(&empty[st], ph ^ 1u);
+            mbar_wait(&empty[st], ph ^ 1u); // every lane acquires the stage itself before it issues a bulk copy into it
             __syncwarp();
             if (done) {
                 // tell one consumer warp that the tiles are gone; every consumer warp needs its own notice
@@ -450,8 +450,10 @@ __global__ void __launch_bounds__((TMA_MAX_WARPS + 1) * 32, 1) ni_step_tma_kerne
                     step_epilogue<T, T, VEC>(s, e, sample, acc[v], ro0, ro1, rx, has_x0, has_x, has_o1);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
+            // hand the stage back: all 32 lanes arrive (count 32), so every lane's shared-memory reads of this stage are ordered
+            // before the producer's next bulk copy into it by that lane's own release -- with __syncwarp + one elected arrive
+            // (the usual pipeline idiom) racecheck reports the other 31 lanes' reads as WAR hazards against the async-proxy write
+            mbar_arrive(&empty[st]);
         }
     }
 }

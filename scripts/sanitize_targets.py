@@ -36,6 +36,17 @@ for dt in (torch.float32, torch.float16, torch.bfloat16):
                     _lib.set_option(k, v)
                 fused_step(**kw)
                 n += 1
+# the TMA ring WRAPPING (2 stages, ~3.5 tiles per CTA): stage buffers and claimed-index slots are rewritten while consumers run
+big = (64, 4, 32, 32)
+kwb = dict(x_in=mk(torch.float32, *big), outs=[mk(torch.float32, *big)], a=1.1, b=[-0.5], c_x0=0.7, terms=[(0.1 * (i + 1), mk(torch.float32, *big)) for i in range(3)],
+           gens=[(0.2, 4)], seed=5, keep_gen=[True], per_sample=4096, out_sample_stride=4096, want_sumsq=True)
+_lib.set_option("variant", 2)
+_lib.set_option("tma_max_stages", 2); _lib.set_option("tma_ctas_per_sm", 1); _lib.set_option("tma_tile_kb", 2)
+for dyn in (0, 1):
+    _lib.set_option("tma_dynamic", dyn)
+    fused_step(**kwb)
+    n += 1
+_lib.set_option("tma_max_stages", 32); _lib.set_option("tma_ctas_per_sm", 2); _lib.set_option("tma_dynamic", 0)
 _lib.set_option("variant", 0)
 # samplers: CIFAR matrix with the uint8 stage (PIX kernel), DDPM first-order with in-kernel noise + graph replay
 t = ni.CoeffTriple.from_npz(os.path.join(ROOT, "naturaldiffusion_b200", "data", "weights", "step_10_weight_42.npz"))
