@@ -428,6 +428,7 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
     agg = ctx.world * batch * n_batches
     e2e = {"value": agg / (host_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "batches": n_batches, "ms_per_batch": host_ms / n_batches, "cuda_graph_per_batch": graph,
+           "bytes_are_per": f"batch of {batch} samples per GPU (one trajectory; the e2e region is {n_batches} such batches, not bench steps)",
            "device_noise": {"value": agg / (dev_ms * 1e-3), "unit": "samples/s", "ms_per_batch": dev_ms / n_batches, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
                             "note": "aggregated over all ranks (max-over-ranks time); noise drawn on the device from (seed, global sample index) as the "
                                     "reference does with torch.randn on the GPU (src/CIFAR10NaturalInference.py:290): only the result crosses PCIe"},

@@ -499,3 +499,25 @@ def test_bind_rank_cpus_gives_disjoint_slices(monkeypatch):
     assert hostutil.bind_rank_cpus(0, 1) == 16
     monkeypatch.setattr(hostutil, "gpu_local_cpus", lambda i: None)
     assert hostutil.bind_rank_cpus(0, 8) is None
+
+
+def test_multiply_shift_sample_index_formula():
+    """the specialised step kernels get the sample index of a CTA as umulhi(blockIdx, mul) >> shr (csrc/ni_step_lean.cuh
+    `fast_divisor`); the same arithmetic in Python is exact for every block index below 2^31"""
+    rng = np.random.default_rng(0)
+
+    def fast_divisor(d):
+        if d <= 1:
+            return 0, 0
+        lg = int(np.ceil(np.log2(d)))
+        if (1 << lg) < d:
+            lg += 1
+        p = 31 + lg
+        return ((1 << p) + d - 1) // d, p - 32
+
+    for d in list(range(1, 300)) + [384, 768, 1000, 4097, 65535, 65536, 1 << 20, (1 << 24) - 1]:
+        mul, shr = fast_divisor(d)
+        assert mul < (1 << 32)
+        ns = np.concatenate([np.arange(0, 2000), rng.integers(0, 1 << 31, 2000), [(1 << 31) - 1, d - 1, d, 2 * d - 1]]).astype(np.uint64)
+        q = ns if mul == 0 else ((ns * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(shr)
+        assert np.array_equal(q, ns // np.uint64(d)), d
