@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(NI_BLOCK, (VB == 32 ? 6 : PIX ? 8 : (NG >= 1 &
         const uint32_t q = g - sample * s.hw_vec;
         pdl_wait();
         uint8_t b[12];
-        float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const uint32_t v = sample * s.vec_per_sample + c * s.hw_vec + q;
@@ -180,10 +179,8 @@ __global__ void __launch_bounds__(NI_BLOCK, (VB == 32 ? 6 : PIX ? 8 : (NG >= 1 &
             lean_vector<T, TO, NT, NG, M, POL, CAP, VB>(s, tab, v, v + sample * s.out_extra_vec, acc);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                const float r = round_to<T>(acc[p]);
-                const float y = (r * s.px_scale + s.px_shift) * 255.0f;
+                const float y = (round_to<T>(acc[p]) * s.px_scale + s.px_shift) * 255.0f;
                 b[p * 3 + c] = (uint8_t)(int)fminf(fmaxf(y, 0.f), 255.f);
-                ss = fmaf(r, r, ss);
             }
         }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -196,7 +193,6 @@ __global__ void __launch_bounds__(NI_BLOCK, (VB == 32 ? 6 : PIX ? 8 : (NG >= 1 &
             const uint4 o = *reinterpret_cast<const uint4 *>(ws + lane * 4);
             st128(s.pixels + (size_t)g0 * 12 + lane * 16, o);
         }
-        (void)ss;
         return;
     } else {
         const uint32_t v = blockIdx.x * NI_BLOCK + threadIdx.x;
