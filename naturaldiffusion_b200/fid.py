@@ -14,9 +14,15 @@ import torch
 
 
 class FidAccumulator:
-    def __init__(self, dim: int = 2048, device="cuda"):
+    def __init__(self, dim: int = 2048, device="cuda", host_logic_only: bool = False):
+        """device: a CUDA device -- the statistics live on that GPU and `update` is the fp64 tensor-core kernel.  There is no
+        silent CPU path: a CPU device is refused unless `host_logic_only=True` is passed explicitly, which exists for the
+        world-size-2 gloo tests of the merge / finalize logic (tests/test_multirank_cpu.py) and computes with plain torch."""
         self.dim = dim
         self.device = torch.device(device)
+        if self.device.type != "cuda" and not host_logic_only:
+            from ._lib import NiError
+            raise NiError("FidAccumulator needs a CUDA device; there is no CPU fallback (host_logic_only=True is for the gloo tests)")
         # one flat fp64 buffer so the merge is a single all-reduce: [n | sum x (d) | sum x x^T (d*d)]
         self.buf = torch.zeros(1 + dim + dim * dim, dtype=torch.float64, device=self.device)
 

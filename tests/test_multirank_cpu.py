@@ -27,7 +27,7 @@ def _worker(rank, world, port, tmp):
         # --- FID statistics: every rank holds a different shard of the activations
         feats = np.load(os.path.join(tmp, "feats.npy"))
         lo, hi = shard_range(feats.shape[0], rank, world)
-        acc = FidAccumulator(dim=feats.shape[1], device="cpu")
+        acc = FidAccumulator(dim=feats.shape[1], device="cpu", host_logic_only=True)
         for i in range(lo, hi, 37):  # ragged micro-batches
             acc.update(torch.from_numpy(feats[i:min(hi, i + 37)]).float())
         acc.all_reduce()
@@ -78,8 +78,14 @@ def test_frechet_distance_known_answers():
 def test_accumulator_single_process_matches_numpy():
     rng = np.random.default_rng(2)
     feats = rng.standard_normal((500, 32)).astype(np.float32)
-    acc = FidAccumulator(dim=32, device="cpu")
+    acc = FidAccumulator(dim=32, device="cpu", host_logic_only=True)
     acc.update(torch.from_numpy(feats[:123])).update(torch.from_numpy(feats[123:])).all_reduce()
     mu, sigma = acc.finalize()
     assert np.abs(mu - feats.astype(np.float64).mean(0)).max() < 1e-12
     assert np.abs(sigma - np.cov(feats.astype(np.float64), rowvar=False)).max() < 1e-10
+
+
+def test_fid_accumulator_refuses_a_silent_cpu_path():
+    from naturaldiffusion_b200 import NiError
+    with pytest.raises(NiError):
+        FidAccumulator(dim=8, device="cpu")
