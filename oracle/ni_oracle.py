@@ -667,7 +667,10 @@ def dpm_solver_original_sample(eps_model, noise, steps, algorithm="dpmsolver++",
     cum = [0]
     for o in orders:
         cum.append(cum[-1] + o)
-    timesteps_outer = ns.time_steps(skip_type, t_T, t_0, steps)[torch.tensor(cum)]
+    if skip_type == "logSNR":  # "To reproduce the results in DPM-Solver paper" (:534-536): K outer nodes uniform in logSNR
+        timesteps_outer = ns.time_steps(skip_type, t_T, t_0, len(orders))
+    else:
+        timesteps_outer = ns.time_steps(skip_type, t_T, t_0, steps)[torch.tensor(cum)]
     for step, o in enumerate(orders):
         s, t = timesteps_outer[step], timesteps_outer[step + 1]
         inner = ns.time_steps(skip_type, float(s), float(t), o)

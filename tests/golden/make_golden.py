@@ -225,9 +225,19 @@ def gen_solver_matrices():
     torch.set_default_dtype(torch.float64)
     out = {}
     try:
-        for K in (5, 10, 15):
-            for alg in ("dpmsolver", "dpmsolver++"):
-                for method, order in (("multistep", 2), ("multistep", 3), ("singlestep", 2), ("singlestep", 3)):
+        settings = [(K, alg, method, order, "time_quadratic", False) for K in (5, 10, 15) for alg in ("dpmsolver", "dpmsolver++")
+                    for method, order in (("multistep", 2), ("multistep", 3), ("singlestep", 2), ("singlestep", 3))]
+        # beyond the FID-table settings: the other time grids of get_time_steps, the fixed-order singlestep driver, the
+        # lower_order_final tail (the library default) and first order (= DDIM)
+        settings += [(10, alg, method, 3, skip, False) for alg in ("dpmsolver", "dpmsolver++") for method in ("multistep", "singlestep")
+                     for skip in ("time_uniform", "logSNR")]
+        settings += [(9, "dpmsolver++", "singlestep_fixed", 3, "time_uniform", False), (8, "dpmsolver", "singlestep_fixed", 2, "logSNR", False),
+                     (7, "dpmsolver++", "multistep", 3, "time_uniform", True), (6, "dpmsolver", "multistep", 2, "time_quadratic", True),
+                     (10, "dpmsolver++", "multistep", 1, "time_uniform", False), (11, "dpmsolver", "singlestep", 3, "time_quadratic", False),
+                     (13, "dpmsolver++", "singlestep", 3, "time_quadratic", False)]
+        for K, alg, method, order, skip, lof in settings:
+            if True:
+                if True:
                     ns = dpm.NoiseScheduleVP("linear", continuous_beta_0=0.1, continuous_beta_1=20.0)
                     rows, nodes = [], []
 
@@ -244,14 +254,14 @@ def gen_solver_matrices():
                     solver = dpm.DPM_Solver(noise_fn, ns, algorithm_type=alg)
                     x0 = torch.zeros(1, 2 * K + 1)
                     x0[0, K] = 1.0
-                    xe = solver.sample(x0, steps=K, t_start=1.0, t_end=1e-3, order=order, skip_type="time_quadratic", method=method,
-                                       denoise_to_zero=False, lower_order_final=False)
+                    xe = solver.sample(x0, steps=K, t_start=1.0, t_end=1e-3, order=order, skip_type=skip, method=method,
+                                       denoise_to_zero=False, lower_order_final=lof)
                     rows.append(xe[0].clone())
                     t_end = torch.tensor([1e-3])
                     nodes.append([1e-3, float(ns.marginal_alpha(t_end)), float(ns.marginal_std(t_end))])
                     assert len(rows) == K and len(nodes) == K + 1, (K, alg, method, order, len(rows), len(nodes))
                     M = torch.stack(rows).numpy()
-                    key = f"{alg}/{method}{order}/{K:03d}"
+                    key = f"{alg}/{method}{order}/{K:03d}" if (skip == "time_quadratic" and not lof) else f"{alg}/{method}{order}/{K:03d}/{skip}/lof{int(lof)}"
                     out[key + "/A"], out[key + "/B"], out[key + "/node"] = M[:, :K], M[:, K:], np.array(nodes)
     finally:
         torch.set_default_dtype(torch.float32)

@@ -15,15 +15,26 @@ from naturaldiffusion_b200 import generators as G
 from oracle import ni_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "solver_matrices.npz")
-SETTINGS = [(K, alg, method, order) for K in (5, 10, 15) for alg in ("dpmsolver", "dpmsolver++")
-            for method, order in (("multistep", 2), ("multistep", 3), ("singlestep", 2), ("singlestep", 3))]
+
+
+def _settings(z):
+    """(key, K, algorithm, method, order, skip_type, lower_order_final) of every matrix in the golden file: the 24 FID-table
+    settings (5/10/15 steps, time_quadratic) plus the other time grids, the fixed-order singlestep driver, the
+    lower_order_final tail and first order"""
+    out = []
+    for key in sorted(set(k.rsplit("/", 1)[0] for k in z.files)):
+        parts = key.split("/")
+        skip, lof = ("time_quadratic", False) if len(parts) == 3 else (parts[3], parts[4] == "lof1")
+        out.append((key, int(parts[2]), parts[0], parts[1][:-1], int(parts[1][-1]), skip, lof))
+    return out
 
 
 def test_dpm_solver_generators_match_the_reference_solver_class():
     z = np.load(GOLD)
-    for K, alg, method, order in SETTINGS:
-        t = G.dpm_solver_triple(K, alg, method, order)
-        key = f"{alg}/{method}{order}/{K:03d}"
+    settings = _settings(z)
+    assert len(settings) == 39
+    for key, K, alg, method, order, skip, lof in settings:
+        t = G.dpm_solver_triple(K, alg, method, order, skip_type=skip, lower_order_final=lof)
         scale = max(1.0, np.abs(z[key + "/A"]).max())
         assert np.abs(t.A - z[key + "/A"]).max() < 1e-11 * scale, key
         assert np.abs(t.B - z[key + "/B"]).max() < 1e-11 * scale, key
@@ -34,7 +45,9 @@ def test_dpm_solver_generators_match_the_reference_solver_class():
 def test_oracle_dpm_solver_restatement_matches_the_reference_solver_class():
     """the oracle's tensor-level sample() run in coefficient space (fp64) reproduces the same goldens"""
     z = np.load(GOLD)
-    for K, alg, method, order in SETTINGS:
+    for key, K, alg, method, order, skip, lof in _settings(z):
+        if method == "singlestep_fixed":
+            continue  # the oracle restates the two drivers the FID runs use
         ns = O._VPSchedule(torch.float64)
         rows, calls = [], [0]
 
@@ -48,10 +61,9 @@ def test_oracle_dpm_solver_restatement_matches_the_reference_solver_class():
 
         x0 = torch.zeros(1, 2 * K + 1, dtype=torch.float64)
         x0[0, K] = 1.0
-        xe = O.dpm_solver_original_sample(eps_model, x0, K, alg, method, order, dtype=torch.float64)
+        xe = O.dpm_solver_original_sample(eps_model, x0, K, alg, method, order, skip_type=skip, lower_order_final=lof, dtype=torch.float64)
         rows.append(xe[0])
         M = torch.stack(rows).numpy()
-        key = f"{alg}/{method}{order}/{K:03d}"
         scale = max(1.0, np.abs(z[key + "/A"]).max())
         assert calls[0] == K and np.abs(M[:, :K] - z[key + "/A"]).max() < 1e-11 * scale and np.abs(M[:, K:] - z[key + "/B"]).max() < 1e-11 * scale, key
 
