@@ -488,7 +488,7 @@ def deis_tab_coefficients(ts, ab_order=3, num_item=10000, b0=0.1, b1=20.0):
 @torch.no_grad()
 def deis_tab_original_loop(ts, eps_model, noise, ab_order=3):
     """th_deis tAB sampler (deps/th_deis/multistep.py:98-104 `ab_step`, driven as in src/AnalyzeDEIS.py:42-58)."""
-    coef = torch.from_numpy(deis_tab_coefficients(ts, ab_order)).to(torch.float32)
+    coef = torch.from_numpy(deis_tab_coefficients(ts, ab_order)).to(noise.dtype)
     x = noise.clone()
     eps_pred = [x] * ab_order
     for i in range(len(ts) - 1):
@@ -687,9 +687,9 @@ def dpm_solver_original_sample(eps_model, noise, steps, algorithm="dpmsolver++",
 
 # --------------------------------------------------------------------------------------
 # DEIS rho-AB, rho-RK and iPNDM (deps/th_deis/sampler.py:50-160, rk.py, multistep.py): original loops on tensors.
-# th_deis is jax code (absent here): restated; no reference output exists to pin these three beyond (i) the shared
-# Adams-Bashforth coefficient routine, which reproduces the shipped results/deis/deis_tab_* matrices, and (ii) the classical
-# AB / RK / linear-multistep tables they reduce to -- "parity unpinned" for rho_ab / rho_rk / ipndm.
+# th_deis is jax code and jax is not installed here: restated, and pinned in tests/test_solver_family.py by running THESE loops in
+# coefficient space against matrices produced by the reference's own th_deis executed with a numpy-backed stand-in for jax
+# (oracle/jax_numpy_shim.py, tests/golden/deis_matrices.npz: 38 settings).
 # --------------------------------------------------------------------------------------
 def _deis_abar(t, b0=0.1, b1=20.0):
     t = np.asarray(t, dtype=np.float64)
@@ -736,7 +736,7 @@ def deis_rho_ab_coefficients(rhos, ab_order=3, num_item=10000):
 @torch.no_grad()
 def deis_original_sample(eps_model, noise, num_step, method="rho_rk", ab_order=3, rk_method="3kutta", ts_phase="t", ts_order=2):
     """th_deis.get_sampler(...)(noise) for method rho_ab | rho_rk | ipndm (t_ab: deis_tab_original_loop above)."""
-    f32 = lambda v: torch.tensor(float(v), dtype=torch.float32, device=noise.device)
+    f32 = lambda v: torch.tensor(float(v), dtype=noise.dtype, device=noise.device)  # th_deis hands torch the coefficients in the tensors' dtype
     if method == "ipndm":  # sampler.py:50-95
         ts = deis_rev_ts(num_step, 1, "t")
         lin = [[1.0, 0, 0, 0], [1.5, -0.5, 0, 0], [23 / 12.0, -16 / 12.0, 5 / 12.0, 0], [55 / 24.0, -59 / 24.0, 37 / 24.0, -9 / 24.0]]

@@ -136,3 +136,25 @@ def dpm_solver_module():
     """deps/dpm_solver_pytorch.py (pure torch): NoiseScheduleVP, DPM_Solver -- the original samplers behind
     results/FID/dpmsolver*_*.csv."""
     return _load(os.path.join(REF_ROOT, "deps", "dpm_solver_pytorch.py"), "_ref_dpm_solver")
+
+
+def th_deis_module():
+    """deps/th_deis (the DEIS samplers behind results/FID/deis_*step.csv; jax code) imported with oracle/jax_numpy_shim.py standing
+    in for jax: numpy float64 arithmetic, complex-step `grad`, loop `vmap`."""
+    from . import jax_numpy_shim
+    saved = {n: sys.modules.get(n) for n in ("jax", "jax.numpy")}
+    saved_path = list(sys.path)
+    try:
+        jax_numpy_shim.install()
+        sys.path.insert(0, os.path.join(REF_ROOT, "deps"))
+        for m in [m for m in sys.modules if m == "th_deis" or m.startswith("th_deis.")]:
+            sys.modules.pop(m)
+        import importlib
+        return importlib.import_module("th_deis")
+    finally:
+        sys.path[:] = saved_path
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m

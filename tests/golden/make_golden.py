@@ -268,11 +268,55 @@ def gen_solver_matrices():
     np.savez_compressed(os.path.join(HERE, "solver_matrices.npz"), **out)
 
 
+def gen_deis_matrices():
+    """Coefficient matrices of the ORIGINAL DEIS samplers, obtained by running the reference's own `th_deis.get_sampler`
+    (deps/th_deis, unmodified) in coefficient space, with oracle/jax_numpy_shim.py standing in for jax (not installed here):
+    numpy float64 arithmetic, complex-step grad, loop vmap.  Settings of src/CIFAR10NaturalInference.py:166-178 (the rows of
+    results/FID/deis_*step.csv: ts_phase t | rho, ts_order 2, t_ab | rho_ab | rho_rk, ab_order 2 | 3) plus iPNDM, Heun's
+    second-order RK and the `log` time grid."""
+    tdeis = ref_loader.th_deis_module()
+    t2a, a2t = tdeis.get_linear_alpha_fns(0.1, 20.0)
+    sde = tdeis.VPSDE(t2a, a2t, 1e-3, 1.0)
+    stages = {"3kutta": 3, "2heun": 2, "4rk": 4, "3heun": 3}
+    settings = [(n, m, o, ph, "3kutta") for n in (5, 10, 15) for ph in ("t", "rho") for m in ("t_ab", "rho_ab") for o in (2, 3)]
+    settings += [(n, "rho_rk", 3, ph, "3kutta") for n in (5, 10, 15) for ph in ("t", "rho")]
+    settings += [(n, "ipndm", 3, "t", "3kutta") for n in (5, 10, 15)]
+    settings += [(6, "rho_rk", 3, "t", "2heun"), (4, "rho_rk", 3, "t", "4rk"), (5, "rho_rk", 3, "log", "3heun"), (8, "rho_ab", 3, "log", "3kutta"),
+                 (8, "t_ab", 1, "t", "3kutta")]
+    out = {}
+    for num_step, method, ab_order, ts_phase, rk in settings:
+        nfe = num_step * stages[rk] if method == "rho_rk" else num_step
+        rows, nodes = [], []
+
+        def eps_fn(x, t):
+            tt = float(t)
+            if nodes:
+                rows.append(x[0].clone())
+            j = len(nodes)
+            ab = float(t2a(np.float64(tt)))
+            nodes.append([tt, np.sqrt(ab), np.sqrt(1.0 - ab)])
+            y = torch.zeros_like(x)
+            y[0, j] = 1.0
+            return (x - np.sqrt(ab) * y) / np.sqrt(1.0 - ab)
+
+        x0 = torch.zeros(1, 2 * nfe + 1, dtype=torch.float64)
+        x0[0, nfe] = 1.0
+        xe = tdeis.get_sampler(sde, eps_fn, ts_phase, 2, num_step, method=method, ab_order=ab_order, rk_method=rk)(x0)
+        rows.append(xe[0].clone())
+        assert len(rows) == nfe and len(nodes) == nfe, (method, num_step, len(rows), len(nodes))
+        M = torch.stack(rows).numpy()
+        key = f"{method}/{num_step:03d}/order{ab_order}/{ts_phase}/{rk}"
+        out[key + "/A"], out[key + "/B"], out[key + "/node"] = M[:, :nfe], M[:, nfe:], np.array(nodes)
+    np.savez_compressed(os.path.join(HERE, "deis_matrices.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "solvers":
         gen_solver_matrices()
+        gen_deis_matrices()
         raise SystemExit(0)
     gen_solver_matrices()
+    gen_deis_matrices()
     gen_weights()
     gen_cifar()
     gen_validate()

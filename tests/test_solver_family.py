@@ -3,8 +3,9 @@ coefficient matrices.  The generators (product, coefficient space)
 restatements of the ORIGINAL loops are written independently; both are pinned here:
   * DPM-Solver / DPM-Solver++ multistep-2/3 and singlestep-2/3 on the 5/10/15-step quadratic grids against matrices that
     tests/golden/make_golden.py obtained from the reference's unmodified DPM_Solver class (solver_matrices.npz);
-  * DEIS rho-AB / rho-RK / iPNDM (th_deis is jax: nothing to run here) against each other and against the classical
-    Adams-Bashforth / Runge-Kutta tables they reduce to."""
+  * DEIS t-AB / rho-AB / rho-RK / iPNDM against matrices obtained from the reference's unmodified th_deis executed with a
+    numpy-backed stand-in for jax (deis_matrices.npz), against each other and against the classical Adams-Bashforth /
+    Runge-Kutta tables they reduce to."""
 import os
 
 import numpy as np
@@ -91,6 +92,63 @@ def test_deis_matrices_equal_the_original_loops(method, kw):
         a = _apply_matrix(t, eps_model, noise)
         b = O.deis_original_sample(eps_model, noise, n, method, **kw)
         assert float((a - b).abs().max() / b.norm()) < 2e-6, (method, kw, n)
+
+
+DEIS_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deis_matrices.npz")
+
+
+def _deis_settings(z):
+    out = []
+    for key in sorted(set(k.rsplit("/", 1)[0] for k in z.files)):
+        m, n, o, ph, rk = key.split("/")
+        out.append((key, m, int(n), int(o[5:]), ph, rk))
+    return out
+
+
+def test_deis_generators_match_the_reference_th_deis():
+    """38 settings traced from the reference's own th_deis.get_sampler (executed with the numpy stand-in for jax): t_ab / rho_ab
+    order 2 and 3 and rho_rk (Kutta) at 5/10/15 steps on the `t` and `rho` grids -- the rows of results/FID/deis_*step.csv --
+    plus iPNDM, other tableaus and the `log` grid"""
+    z = np.load(DEIS_GOLD)
+    settings = _deis_settings(z)
+    assert len(settings) == 38
+    for key, m, n, o, ph, rk in settings:
+        t = G.deis_triple(n, m, ab_order=o, rk_method=rk, ts_phase=ph)
+        scale = max(1.0, np.abs(z[key + "/A"]).max())
+        assert np.abs(t.A - z[key + "/A"]).max() < 1e-11 * scale, key
+        assert np.abs(t.B - z[key + "/B"]).max() < 1e-11 * scale, key
+        assert np.abs(t.node[:-1] - z[key + "/node"]).max() < 1e-12, key
+
+
+def test_oracle_deis_loops_match_the_reference_th_deis():
+    """the oracle's tensor-level DEIS loops run in coefficient space (fp64) against the same goldens"""
+    z = np.load(DEIS_GOLD)
+    for key, m, n, o, ph, rk in _deis_settings(z):
+        if rk not in ("3kutta", "2heun", "4rk", "3heun"):
+            continue
+        K = z[key + "/A"].shape[0]
+        rows, calls = [], [0]
+
+        def eps_model(x, t):
+            if calls[0] > 0:
+                rows.append(x[0].clone())
+            ab = float(O._deis_abar(t))
+            y = torch.zeros_like(x)
+            y[0, calls[0]] = 1.0
+            calls[0] += 1
+            return (x - np.sqrt(ab) * y) / np.sqrt(1.0 - ab)
+
+        x0 = torch.zeros(1, 2 * K + 1, dtype=torch.float64)
+        x0[0, K] = 1.0
+        if m == "t_ab":
+            xe = O.deis_tab_original_loop(O.deis_rev_ts(n, 2, ph), eps_model, x0, ab_order=o)
+        else:
+            xe = O.deis_original_sample(eps_model, x0, n, m, ab_order=o, rk_method=rk, ts_phase=ph)
+        rows.append(xe[0])
+        M = torch.stack(rows).numpy()
+        scale = max(1.0, np.abs(z[key + "/A"]).max())
+        assert calls[0] == K, key
+        assert np.abs(M[:, :K] - z[key + "/A"]).max() < 1e-10 * scale and np.abs(M[:, K:] - z[key + "/B"]).max() < 1e-10 * scale, key
 
 
 def test_deis_building_blocks_reduce_to_the_classical_tables():
