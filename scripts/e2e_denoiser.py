@@ -88,6 +88,14 @@ def main():
         res = {"config": args.config, "batch_per_gpu": args.batch, "n_gpus": world, "K": triple.K, "autocast": args.autocast,
                "ours_ms_per_trajectory": ms_ours, "ours_samples_per_s": world * args.batch / (ms_ours * 1e-3),
                "denoiser_only_ms": ms_model, "update_share_ours": max(0.0, 1 - ms_model / ms_ours)}
+        # true end to end with HOST buffers: pinned fp32 noise in (H2D), K x (NCSN++ forward + fused step), uint8 images out (D2H)
+        shape = s.full_shape()
+        nb = 3
+        noise_h = [torch.randn(shape).pin_memory() for _ in range(2)]
+        out_h = [torch.empty((args.batch, 32, 32, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        ms_host = timed(lambda: s.sample_host_many(den, [noise_h[i % 2] for i in range(nb)], [out_h[i % 2] for i in range(nb)], pixels=True), 1) / nb
+        res.update(e2e_host_ms_per_batch=ms_host, e2e_host_samples_per_s=world * args.batch / (ms_host * 1e-3),
+                   e2e_host_bytes_per_batch={"h2d": noise_h[0].numel() * 4, "d2h": out_h[0].numel()})
         if world == 1:
             from naturaldiffusion_b200.ops import philox_normal
             noise = philox_normal(s.full_shape(), seed=888, tensor_id=0, device=dev)
