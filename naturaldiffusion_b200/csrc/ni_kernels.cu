@@ -773,6 +773,7 @@ int ni_step(const NiStepDesc *d, void *stream)
     if (d->numel % d->per_sample != 0) return fail(NI_ERR_INVALID, "ni_step: numel %lld is not a multiple of per_sample %lld", (long long)d->numel, (long long)d->per_sample);
     if (d->n_terms < 0 || d->n_terms > NI_MAX_TERMS) return fail(NI_ERR_TOO_MANY, "ni_step: n_terms=%d exceeds NI_MAX_TERMS=%d (chain launches with accumulate=1)", d->n_terms, NI_MAX_TERMS);
     if (d->n_gen < 0 || d->n_gen > NI_MAX_GEN) return fail(NI_ERR_TOO_MANY, "ni_step: n_gen=%d exceeds NI_MAX_GEN=%d", d->n_gen, NI_MAX_GEN);
+    if ((reinterpret_cast<uintptr_t>(d->elem_offset_dev) & 7u) != 0) return fail(NI_ERR_INVALID, "ni_step: elem_offset_dev must be 8-byte aligned");
     if (d->numel == 0) return NI_OK; // an empty shard: nothing to do (its tensors have NULL data pointers)
     if (d->x_next == nullptr && d->pixels_u8 == nullptr) return fail(NI_ERR_INVALID, "ni_step: x_next is NULL (allowed only with pixels_u8)");
     if (d->pixels_u8 != nullptr && (d->px_channels <= 0 || d->per_sample % d->px_channels != 0)) return fail(NI_ERR_INVALID, "ni_step: pixels_u8 needs px_channels dividing per_sample");
@@ -910,6 +911,7 @@ int ni_weighted_sum(const void *const *src, const double *coeffs, int n_terms, v
 
 static int philox_normal_impl(void *dst, int64_t numel, int dst_dtype, uint64_t seed, uint64_t tensor_id, uint64_t elem_offset, const uint64_t *elem_offset_dev, void *stream)
 {
+    if ((reinterpret_cast<uintptr_t>(elem_offset_dev) & 7u) != 0) return fail(NI_ERR_INVALID, "ni_philox_normal_at: elem_offset_dev must be 8-byte aligned");
     if (numel == 0) return NI_OK;
     if (dst == nullptr || numel < 0) return fail(NI_ERR_INVALID, "ni_philox_normal: bad arguments");
     const int ds = dtype_size(dst_dtype);
@@ -945,7 +947,7 @@ int ni_philox_normal_at(void *dst, int64_t numel, int dst_dtype, uint64_t seed, 
 
 int ni_counter_add(uint64_t *counter_dev, uint64_t delta, void *stream)
 {
-    if (counter_dev == nullptr) return fail(NI_ERR_INVALID, "ni_counter_add: NULL counter");
+    if (counter_dev == nullptr || (reinterpret_cast<uintptr_t>(counter_dev) & 7u) != 0) return fail(NI_ERR_INVALID, "ni_counter_add: counter must be a non-NULL, 8-byte aligned device pointer");
     ni_counter_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(counter_dev, delta);
     return check_launch("ni_counter_add launch");
 }

@@ -113,3 +113,17 @@ def test_graphed_host_pipeline_equals_the_launch_by_launch_pipeline(weights_dir,
             assert torch.equal(x, y)
         if nh is None:
             assert not torch.equal(a[0], a[1])
+
+
+def test_device_counter_arguments_are_validated():
+    from naturaldiffusion_b200 import _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    buf = torch.zeros(4, dtype=torch.int64, device=DEV)
+    dst = torch.empty(64, device=DEV)
+    assert L.ni_counter_add(None, 4, st) == -1
+    assert L.ni_counter_add(buf.data_ptr() + 4, 4, st) == -1
+    assert L.ni_philox_normal_at(dst.data_ptr(), 64, 0, 1, 0, 0, buf.data_ptr() + 4, st) == -1
+    assert L.ni_counter_add(buf.data_ptr(), 5, st) == 0 and L.ni_counter_add(buf.data_ptr(), 7, st) == 0
+    torch.cuda.synchronize()
+    assert int(buf[0]) == 12
