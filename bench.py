@@ -243,11 +243,14 @@ def measured_peak():
 
 def kernel_source_sha():
     """hash of the sources of the dominant kernel (the specialised step kernels and the shared device helpers)"""
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, "naturaldiffusion_b200", "csrc")
     for n in sorted(os.listdir(d)):
         if n.startswith("ni_step_lean") or n == "ni_common.cuh":
-            h.update(open(os.path.join(d, n), "rb").read())
+            src = open(os.path.join(d, n), "r").read()
+            src = re.sub(r"//[^\n]*", "", src)          # comments and layout do not change the kernels
+            h.update("".join(src.split()).encode())
     return h.hexdigest()[:16]
 
 

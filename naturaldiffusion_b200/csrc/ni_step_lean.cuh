@@ -1,7 +1,7 @@
 // ni_step_lean.cuh -- the production instantiations of the fused Natural Inference step (ni_step, include/ni_b200.h).
 //
 // Same arithmetic, same accumulation order and therefore the same bits as the generic kernel in ni_kernels.cu
-// (tests/test_gpu_parity.py::test_lean_kernel_is_bit_identical_to_generic), with the per-thread overhead removed.  The
+// (tests/test_gpu_lean.py::test_lean_kernel_is_bit_identical_to_generic), with the per-thread overhead removed.  The
 // generic kernel executes ~210 SASS instructions per thread on a 7-tensor step (64-bit index arithmetic, a 64-bit
 // division per thread for the sample index, runtime loops over constant-bank tables); at 30 instructions per 16 B moved
 // the SMs burn enough power for the 1 kW cap to pull the clock down in sustained runs.  Here:
@@ -13,7 +13,8 @@
 //   * Philox round keys expanded on the host; -2 ln u through MUFU.LG2 with a series near u = 1 (ni_common.cuh);
 //   * the fused uint8 output stage (last step) has its own instantiation in which a thread owns the C = 3 channel
 //     planes of 4 consecutive pixels, the warp stages its 384 bytes in shared memory and stores them as 24 x 16 B.
-// Still an HBM-streaming kernel: no tensor cores, one 128-bit load per tensor per thread, all issued before the first FMA.
+//   * 128-bit or, on Blackwell, 256-bit global accesses per thread per tensor (NI_LEAN_WIDE below).
+// Still an HBM-streaming kernel: no tensor cores, one vector load per tensor per thread, all issued before the first FMA.
 #pragma once
 #include "ni_common.cuh"
 
