@@ -127,3 +127,36 @@ def test_device_counter_arguments_are_validated():
     assert L.ni_counter_add(buf.data_ptr(), 5, st) == 0 and L.ni_counter_add(buf.data_ptr(), 7, st) == 0
     torch.cuda.synchronize()
     assert int(buf[0]) == 12
+
+
+def test_graphed_host_pipeline_with_a_stochastic_matrix_advances_fresh_noise():
+    """host noise in + DDPM fresh noise drawn in-kernel: every batch of the graphed pipeline draws its own eps_1..K (device
+    counter advanced inside the graph) and equals the launch-by-launch pipeline"""
+    g = torch.Generator().manual_seed(9)
+    noises = [torch.randn(8, 4, 16, 16, generator=g).pin_memory() for _ in range(4)]
+    new_out = lambda: [torch.empty(8, 4, 16, 16).pin_memory() for _ in range(4)]
+    a, b = new_out(), new_out()
+    _ddpm(8).sample_host_many(den, noises, a, first_sample=16)
+    s = _ddpm(8)
+    s.sample_host_many(den, noises, b, first_sample=16, graph=True)
+    s.sample_host_many(den, noises, b, first_sample=16, graph=True)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    # same host noise in batches 0 and 1 would still give different samples: the fresh noise differs
+    same = [noises[0], noises[0]]
+    o = new_out()[:2]
+    _ddpm(8).sample_host_many(den, same, o)
+    torch.cuda.synchronize()
+    assert not torch.equal(o[0], o[1])
+
+
+def test_in_kernel_noise_passes_a_kolmogorov_smirnov_test():
+    from scipy import stats
+    z = philox_normal((1 << 20,), seed=12345, tensor_id=77, device=DEV).cpu().numpy().astype(np.float64)
+    ks = stats.kstest(z, "norm")
+    assert ks.statistic < 2.5e-3, ks
+    assert abs(stats.skew(z)) < 0.01 and abs(stats.kurtosis(z)) < 0.02
+    # independence across tensor ids and neighbouring elements
+    z2 = philox_normal((1 << 20,), seed=12345, tensor_id=78, device=DEV).cpu().numpy().astype(np.float64)
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 5e-3 and abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 5e-3
