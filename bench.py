@@ -464,6 +464,7 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
                                "how": f"bare cudaMemcpyAsync of the same {h2d} B H2D + {d2h} B D2H per batch on the pipeline's own two copy streams, "
                                       f"all {ctx.world} rank(s) at once, max over ranks"}
         e2e["frac_of_copy_ceiling"] = e2e["value"] / ceil_sps
+        e2e["copy_ceiling_gbs"] = e2e["copy_ceiling"]["gbs_aggregate"]
         # the device-noise variant only returns results: its ceiling is the D2H direction alone
         def d2h_only(n):
             for i in range(n):
