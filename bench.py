@@ -15,7 +15,9 @@ One bench STEP = a block of trajectories sized for >= 50 ms (128 C2 trajectories
             steps (one CUDA graph per batch) -> fused uint8 pixel stage -> D2H, copies inside the timed region, >= 64
             batches whatever --steps is; `e2e.device_noise` is the reference's own data flow (noise drawn on the device,
             src/CIFAR10NaturalInference.py:290: only the images cross PCIe), aggregated over ranks; `e2e.copy_ceiling` is
-            the bare cudaMemcpyAsync H2D+D2H rate of the same bytes on the same streams at the same N
+            the bare cudaMemcpyAsync H2D+D2H rate of the same bytes on the same streams at the same N;
+            `e2e.with_score_network` is the same host-buffer call with a real (random-init) NCSN++ in the loop -- the
+            pipeline whose 1 -> 8 GPU scaling the north-star asks for (informational: the torch forward dominates)
   roofline  algorithmic bytes per ni_step launch / mean launch duration (CUDA events over the timed region)
   per_config  the other BASELINE shapes (C3, C4 dense + first-order, C5 default/sharp at B 64 and 256), same measurements
   cpu_baseline / --impl reference: the oracle's torch-CPU restatement of the reference loop
@@ -69,6 +71,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=64)
+    ap.add_argument("--no-score-network", action="store_true", help="skip e2e.with_score_network (real NCSN++ in the loop, ~5 s)")
     ap.add_argument("--no-per-config", action="store_true", help="skip the per_config lines (the other BASELINE shapes)")
     ap.add_argument("--only", default="", help="comma list of per_config labels to run")
     ap.add_argument("--cold", action="store_true", help="run the cold-L2 per-launch check on c4/c5 too (default: c2/c3 only)")
@@ -502,6 +505,47 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
     return e2e
 
 
+def e2e_score_network_arm(ctx, batch=512, n_batches=2):
+    """End to end with HOST buffers and a REAL score network in the loop: pinned fp32 noise H2D -> K x (NCSN++ forward in torch +
+    one fused ni_step) -> fused uint8 stage -> D2H, through NaturalInferenceSampler.sample_host_many.  The network is the
+    reference's CIFAR-10 architecture (deps/score_sde_pytorch configs/vp/cifar10_ddpmpp_continuous.py, 61.8 M parameters) with
+    random weights (no checkpoint offline); its forward stays torch by the north-star and dominates the time, so this is
+    not a kernel number -- it is the end-to-end pipeline whose 1 -> 8 GPU scaling the north-star asks for, where the null
+    denoiser of `e2e.value` is a PCIe stress test instead."""
+    import naturaldiffusion_b200 as ni
+    from naturaldiffusion_b200.adapters import ncsnpp_denoiser
+    from naturaldiffusion_b200.denoisers import NCSNppVP
+    from naturaldiffusion_b200.sampler import NaturalInferenceSampler
+    torch = ctx.torch
+    triple = ni.CoeffTriple.from_npz(os.path.join(WEIGHTS, CONFIGS["c2"][0]))
+    torch.manual_seed(0)
+    model = NCSNppVP().reinit_output().to(ctx.dev).eval()
+    den = ncsnpp_denoiser(model, triple.node)
+    s = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), batch, (3, 32, 32), device=ctx.dev, seed=888,
+                                sample_offset=ctx.rank * batch, advance=ctx.world * batch)
+    noise_h = [torch.randn(s.full_shape()).pin_memory() for _ in range(2)]
+    out_h = [torch.empty((batch, 32, 32, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    run = lambda n: s.sample_host_many(den, [noise_h[i % 2] for i in range(n)], [out_h[i % 2] for i in range(n)], pixels=True)
+    with torch.no_grad():
+        run(1)
+        ctx.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(n_batches)
+        b.record()
+        ctx.barrier()
+    ms = ctx.max_over_ranks(a.elapsed_time(b)) / n_batches
+    n_par = sum(p.numel() for p in model.parameters())
+    res = {"value": ctx.world * batch / (ms * 1e-3), "unit": "samples/s", "ms_per_batch": ms, "batch_per_gpu": batch, "batches": n_batches,
+           "h2d_bytes_per_step": noise_h[0].numel() * 4, "d2h_bytes_per_step": out_h[0].numel(), "K": triple.K,
+           "denoiser": f"NCSN++ VP (random init, {n_par / 1e6:.1f} M parameters, fp32, eager torch)",
+           "note": "informational: the torch forward dominates (the fused step is < 1 % of the batch); reported because it is the end-to-end "
+                   "pipeline that scales with GPUs, while the null-denoiser e2e above is bound by the host's copy bandwidth"}
+    del s, model
+    torch.cuda.empty_cache()
+    return res
+
+
 def fid_arm(ctx):
     """The evaluation step behind the sampler: fp64 sufficient statistics of 2048-d activations on the fp64
     tensor cores (csrc/ni_fid.cu) and, at N > 1, the ONE collective of the north-star -- the all-reduce of the 34 MB
@@ -739,6 +783,8 @@ def run_ours(args, rank, world, local_rank):
         del w
         torch.cuda.empty_cache()
         line["fid"] = fid_arm(ctx)
+        if e2e is not None and not args.no_score_network:
+            e2e["with_score_network"] = e2e_score_network_arm(ctx)
         if world == 1:
             line["samplers_via_matrix"] = samplers_via_matrix(ctx)
 

@@ -962,8 +962,9 @@ int ni_debug_box_muller(const uint32_t *ra, const uint32_t *rb, float *za, float
 
 int ni_to_pixel_u8(const void *x, int src_dtype, uint8_t *dst, int64_t batch, int channels, int height, int width, float scale, float shift, void *stream)
 {
-    if (x == nullptr || dst == nullptr || batch < 0 || channels <= 0 || height <= 0 || width <= 0) return fail(NI_ERR_INVALID, "ni_to_pixel_u8: bad arguments");
-    if (batch == 0) return NI_OK;
+    if (batch < 0 || channels <= 0 || height <= 0 || width <= 0) return fail(NI_ERR_INVALID, "ni_to_pixel_u8: bad sizes");
+    if (batch == 0) return NI_OK; // an empty shard: its tensors have NULL data pointers
+    if (x == nullptr || dst == nullptr) return fail(NI_ERR_INVALID, "ni_to_pixel_u8: NULL pointer");
     const int64_t HW = (int64_t)height * width, npix = batch * HW;
     const unsigned blocks = (unsigned)((npix + NI_BLOCK - 1) / NI_BLOCK);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

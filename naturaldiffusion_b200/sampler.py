@@ -363,6 +363,8 @@ class NaturalInferenceSampler:
         dev_noise = self._eps0.view(shape)
         dev_noise.copy_(noise_host, non_blocking=True)
         if pixels:
+            if len(self.sample_shape) != 3:
+                raise NiError("pixels=True needs a (C,H,W) sample shape")
             if not hasattr(self, "_pix"):
                 b, (c, h, w) = self.batch, self.sample_shape
                 self._pix = torch.empty((b, h, w, c), dtype=torch.uint8, device=self.device)
@@ -389,10 +391,16 @@ class NaturalInferenceSampler:
         shape = self.full_shape()
         dev = self.device
         if not hasattr(self, "_stage"):
-            b, (c, h, w) = self.batch, self.sample_shape
+            if pixels:
+                if len(self.sample_shape) != 3:
+                    raise NiError("pixels=True needs a (C,H,W) sample shape")
+                c, h, w = self.sample_shape
+                out_shape, out_dtype = (self.batch, h, w, c), torch.uint8
+            else:
+                out_shape, out_dtype = shape, self.dtype
             self._stage = dict(
                 noise=[torch.empty(shape, dtype=self.dtype, device=dev) for _ in range(2)],
-                out=[(torch.empty((b, h, w, c), dtype=torch.uint8, device=dev) if pixels else torch.empty(shape, dtype=self.dtype, device=dev)) for _ in range(2)],
+                out=[torch.empty(out_shape, dtype=out_dtype, device=dev) for _ in range(2)],
                 pixels=pixels, h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev), graphs={})
         st = self._stage
         if st["pixels"] != pixels:

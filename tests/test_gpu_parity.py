@@ -171,6 +171,7 @@ def test_edge_sizes_empty_batch_and_64bit_indexing(weights_dir):
     """empty shard (a rank with no samples) is a no-op; element indices beyond 2^31 are addressed correctly"""
     triple, s = _c2_sampler(weights_dir, 0)
     assert s.sample(lambda x, k: x).shape == (0, 3, 32, 32)
+    assert to_pixel_u8(torch.empty(0, 3, 32, 32, device=DEV)).shape == (0, 32, 32, 3)  # NULL data pointers, still a no-op
     n = (1 << 31) + 4096
     src = torch.empty(n, dtype=torch.float16, device=DEV)
     src[:8] = 1.0
@@ -465,6 +466,30 @@ def test_host_buffer_paths_match_device_path(weights_dir):
     torch.cuda.synchronize()
     for n, o in zip(noises, lat):
         assert torch.equal(o, s2.sample(den, noise=n.to(DEV)).cpu())
+
+
+def test_host_buffer_pipeline_with_a_non_image_sample_shape(weights_dir):
+    """the host-buffer pipeline does not assume (C,H,W) samples unless the uint8 pixel stage is asked for: a flat
+    1-D sample shape runs through sample_host_many / sample_host and equals the device path; pixels=True refuses it"""
+    den = lambda x, k: torch.tanh(0.7 * x) * (1.0 + 0.01 * k) + 0.1 * x
+    triple = ni.CoeffTriple.from_npz(os.path.join(weights_dir, "step_10_weight_42.npz"))
+    s = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), 32, (1000,), device=DEV, seed=3)
+    g = torch.Generator().manual_seed(9)
+    noises = [torch.randn(32, 1000, generator=g).pin_memory() for _ in range(3)]
+    outs = [torch.empty(32, 1000).pin_memory() for _ in range(3)]
+    s.sample_host_many(den, noises, outs)
+    torch.cuda.synchronize()
+    for n, o in zip(noises, outs):
+        assert torch.equal(o, s.sample(den, noise=n.to(DEV)).cpu())
+    o1 = torch.empty(32, 1000).pin_memory()
+    s.sample_host(den, noises[1], o1)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, outs[1])
+    s2 = NaturalInferenceSampler(triple, ni.io_score_vp(triple.node), 32, (1000,), device=DEV, seed=3)
+    with pytest.raises(ni.NiError):
+        s2.sample_host_many(den, noises, [torch.empty(32, 1000, dtype=torch.uint8).pin_memory() for _ in range(3)], pixels=True)
+    with pytest.raises(ni.NiError):
+        s2.sample_host(den, noises[0], torch.empty(32, 1000, dtype=torch.uint8).pin_memory(), pixels=True)
 
 
 def test_full_size_c2_linearity(weights_dir):
