@@ -783,10 +783,15 @@ def run_ours(args, rank, world, local_rank):
         del w
         torch.cuda.empty_cache()
         line["fid"] = fid_arm(ctx)
-        if e2e is not None and not args.no_score_network:
-            e2e["with_score_network"] = e2e_score_network_arm(ctx)
         if world == 1:
             line["samplers_via_matrix"] = samplers_via_matrix(ctx)
+
+    if e2e is not None and not args.no_score_network and args.config == "c2":
+        torch.cuda.empty_cache()
+        try:
+            e2e["with_score_network"] = e2e_score_network_arm(ctx)
+        except Exception as ex:  # informational arm: say so in the line instead of losing the line
+            e2e["with_score_network"] = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
         if world > 1:
