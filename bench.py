@@ -76,6 +76,8 @@ def parse():
     ap.add_argument("--only", default="", help="comma list of per_config labels to run")
     ap.add_argument("--cold", action="store_true", help="run the cold-L2 per-launch check on c4/c5 too (default: c2/c3 only)")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold-L2 per-launch check (keeps profiler launch lists to the timed region)")
+    ap.add_argument("--relay", default=None, choices=["auto", "off", "force"], help="host-copy routing at N > 1 (default $NI_HOST_RELAY or auto): relay the "
+                    "host copies of ranks that reach host memory across the socket link through an NVLink peer, if a start-up probe says it pays")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the process to its own slice of the GPU's NUMA node")
     ap.add_argument("--no-check", action="store_true", help="skip the cross-rank bit check (N > 1)")
     ap.add_argument("--eager-comparator", action="store_true", help="also time the reference's eager torch loop on this GPU (c2/c3)")
@@ -285,8 +287,22 @@ class Ctx:
         from naturaldiffusion_b200.hostutil import bind_rank_cpus
         self.all_cpus = os.sched_getaffinity(0)
         self.bound_cpus = None if args.no_numa else bind_rank_cpus(local_rank, world)  # before any pinned allocation
+        self.relay, self.relay_info = {"d2h": None, "bidir": None}, {"mode": "off"}
         if world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            if not args.no_e2e:
+                from naturaldiffusion_b200.hostutil import choose_host_relay
+                self.relay, self.relay_info = choose_host_relay(rank, world, self.dev, mode=args.relay)
+
+    def copy_ceiling_ms(self, h2d, d2h, reps, with_h2d, peer=None):
+        """bare cudaMemcpyAsync of the same bytes, all ranks at once, ms per batch (max over ranks); peer = relay route"""
+        from naturaldiffusion_b200.hostutil import _CopyRig
+        rig = _CopyRig(self.dev, None if peer is None else self.torch.device("cuda", peer), h2d, d2h)
+        rig.run(4, with_h2d)
+        self.barrier()
+        ms = rig.run(reps, with_h2d)
+        self.barrier()
+        return self.max_over_ranks(ms) / reps
 
     def barrier(self):
         if self.world > 1:
@@ -429,8 +445,11 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
         ctx.barrier()
         return ctx.max_over_ranks(a.elapsed_time(b))
 
+    s.set_host_relay(ctx.relay["bidir"])
     host_ms = timed(lambda n: [noise_hs[i % 2] for i in range(n)], n_batches)
+    s.set_host_relay(ctx.relay["d2h"])
     dev_ms = timed(lambda n: None, n_batches)
+    s.set_host_relay(None)
     agg = ctx.world * batch * n_batches
     e2e = {"value": agg / (host_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "batches": n_batches, "ms_per_batch": host_ms / n_batches, "cuda_graph_per_batch": graph,
@@ -440,56 +459,39 @@ def e2e_arm(ctx, w, n_batches, graph=True, ceiling=True):
                                     "reference does with torch.randn on the GPU (src/CIFAR10NaturalInference.py:290): only the result crosses PCIe"},
            "api": f"NaturalInferenceSampler.sample_host_many(pixels={pixels}, graph={graph}), double-buffered copy streams: pinned {dts} noise in, "
                   + ("NHWC uint8 out" if pixels else f"{dts} latent out")}
+    e2e["host_route"] = {"host_noise": ctx.relay["bidir"], "device_noise": ctx.relay["d2h"], "probe": ctx.relay_info,
+                         "what": "GPU index this rank's host copies are relayed through over NVLink (null = its own PCIe link); decided per box by "
+                                 "hostutil.choose_host_relay from the bandwidths in `probe` (rank 0's route shown; the probe lists every pair)"}
     if ceiling:
-        # bare copies of the same bytes on the same two streams, all ranks at once: what the host/PCIe side allows at this N
-        st = s._stage
-        nb, ob = st["noise"], st["out"]
-        def copies(n):
-            for i in range(n):
-                with torch.cuda.stream(st["h2d"]):
-                    nb[i % 2].copy_(noise_hs[i % 2], non_blocking=True)
-                with torch.cuda.stream(st["d2h"]):
-                    out_hs[i % 2].copy_(ob[i % 2], non_blocking=True)
-        main = torch.cuda.current_stream(ctx.dev)
-        copies(4)
-        ctx.barrier()
+        # bare copies of the same bytes, all ranks at once: what the host/PCIe side allows at this N -- over every GPU's own
+        # link ("copy_ceiling") and, when a relay route is in use, over the route the pipeline took ("copy_ceiling_routed")
         n_c = max(16, n_batches // 2)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        st["h2d"].wait_stream(main); st["d2h"].wait_stream(main)
-        copies(n_c)
-        main.wait_stream(st["h2d"]); main.wait_stream(st["d2h"])
-        b.record()
-        ctx.barrier()
-        c_ms = ctx.max_over_ranks(a.elapsed_time(b)) / n_c
+        c_ms = ctx.copy_ceiling_ms(h2d, d2h, n_c, True)
         ceil_sps = ctx.world * batch / (c_ms * 1e-3)
         e2e["copy_ceiling"] = {"samples_per_s": ceil_sps, "gbs_aggregate": ctx.world * (h2d + d2h) / (c_ms * 1e-3) / 1e9, "ms_per_batch": c_ms,
-                               "how": f"bare cudaMemcpyAsync of the same {h2d} B H2D + {d2h} B D2H per batch on the pipeline's own two copy streams, "
+                               "how": f"bare cudaMemcpyAsync of the same {h2d} B H2D + {d2h} B D2H per batch on two copy streams, every GPU over its own PCIe link, "
                                       f"all {ctx.world} rank(s) at once, max over ranks"}
         e2e["frac_of_copy_ceiling"] = e2e["value"] / ceil_sps
         e2e["copy_ceiling_gbs"] = e2e["copy_ceiling"]["gbs_aggregate"]
         # the device-noise variant only returns results: its ceiling is the D2H direction alone
-        def d2h_only(n):
-            for i in range(n):
-                with torch.cuda.stream(st["d2h"]):
-                    out_hs[i % 2].copy_(ob[i % 2], non_blocking=True)
-        d2h_only(4)
-        ctx.barrier()
-        a.record()
-        st["d2h"].wait_stream(main)
-        d2h_only(n_c)
-        main.wait_stream(st["d2h"])
-        b.record()
-        ctx.barrier()
-        d_ms = ctx.max_over_ranks(a.elapsed_time(b)) / n_c
+        d_ms = ctx.copy_ceiling_ms(h2d, d2h, n_c, False)
         d_sps = ctx.world * batch / (d_ms * 1e-3)
         e2e["device_noise"]["copy_ceiling"] = {"samples_per_s": d_sps, "gbs_aggregate": ctx.world * d2h / (d_ms * 1e-3) / 1e9, "ms_per_batch": d_ms,
-                                               "how": f"bare cudaMemcpyAsync D2H of the same {d2h} B per batch, all {ctx.world} rank(s) at once"}
+                                               "how": f"bare cudaMemcpyAsync D2H of the same {d2h} B per batch, every GPU over its own PCIe link, all {ctx.world} rank(s) at once"}
         e2e["device_noise"]["frac_of_copy_ceiling"] = e2e["device_noise"]["value"] / d_sps
+        if ctx.world > 1 and ctx.relay_info.get("pairs") and "relayed_gbs_per_rank" in ctx.relay_info:  # (all ranks agree: the info is built from gathered numbers)
+            r_ms = ctx.copy_ceiling_ms(h2d, d2h, n_c, True, peer=ctx.relay["bidir"])
+            rd_ms = ctx.copy_ceiling_ms(h2d, d2h, n_c, False, peer=ctx.relay["d2h"])
+            e2e["copy_ceiling_routed"] = {"samples_per_s": ctx.world * batch / (r_ms * 1e-3), "gbs_aggregate": ctx.world * (h2d + d2h) / (r_ms * 1e-3) / 1e9, "ms_per_batch": r_ms}
+            e2e["frac_of_copy_ceiling_routed"] = e2e["value"] / e2e["copy_ceiling_routed"]["samples_per_s"]
+            e2e["device_noise"]["copy_ceiling_routed"] = {"samples_per_s": ctx.world * batch / (rd_ms * 1e-3), "gbs_aggregate": ctx.world * d2h / (rd_ms * 1e-3) / 1e9, "ms_per_batch": rd_ms}
+            e2e["device_noise"]["frac_of_copy_ceiling_routed"] = e2e["device_noise"]["value"] / e2e["device_noise"]["copy_ceiling_routed"]["samples_per_s"]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # and with nothing crossing PCIe at all: noise drawn on the device, images consumed on the device (the flow of
         # examples/cifar10_pipeline.py: uint8 images -> features -> FID statistics on the same GPU) -- what the pipeline itself scales like
         if graph:
-            kw = dict(pixels_out=ob[0]) if pixels else dict(out=ob[0])
+            ob0 = torch.empty(out_h.shape, dtype=out_h.dtype, device=ctx.dev)
+            kw = dict(pixels_out=ob0) if pixels else dict(out=ob0)
             g = s.capture(den, **kw)
             for _ in range(4):
                 s.replay(g)

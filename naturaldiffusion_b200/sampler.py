@@ -84,6 +84,7 @@ class NaturalInferenceSampler:
         # the Philox element offset of this shard: a device counter (all descriptors carry its address, their host offset is 0)
         self._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._graphs = {}
+        self._relay_peer: Optional[torch.device] = None
         self.set_sample_offset(sample_offset)
         self.final_scale, self.final_bias = float(final_scale), float(final_bias)
         from .coeffs import markov_ratios
@@ -350,6 +351,27 @@ class NaturalInferenceSampler:
         return g._ni_out
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end)
+    def set_host_relay(self, peer: Optional[int]):
+        """Route the host copies of `sample_host_many` through GPU `peer`: host <-> peer over the PEER's PCIe link, peer <-> this
+        GPU over NVLink (one extra 0.9 TB/s hop).  For boxes where this GPU reaches host memory across the socket
+        interconnect and an NVLink peer sits next to it -- e.g. a single-NUMA-node VM on a two-socket HGX board, where four
+        ranks share ~76 GB/s to host memory and the other four have 177 GB/s (profiles/r02_host_copy_probe_n8.json);
+        `hostutil.choose_host_relay` measures whether it pays and picks the peer.  None = direct copies (default).  Results do
+        not depend on the route.  The peer only runs copy-engine work for this process (a second CUDA context on it)."""
+        if peer is None:
+            new = None
+        else:
+            peer = int(peer)
+            own = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            if peer == own or peer < 0 or peer >= torch.cuda.device_count():
+                raise NiError(f"host relay peer must be another visible GPU (got {peer}, own {own})")
+            if not torch.cuda.can_device_access_peer(own, peer):
+                raise NiError(f"GPU {own} has no peer access to GPU {peer}")
+            new = torch.device("cuda", peer)
+        if new != self._relay_peer and hasattr(self, "_stage"):
+            del self._stage  # staging buffers, streams and per-buffer graphs are rebuilt for the new route
+        self._relay_peer = new
+
     @torch.no_grad()
     def sample_host(self, denoiser: Callable, noise_host: torch.Tensor, out_host: torch.Tensor, pixels: bool = False):
         """End-to-end call with HOST buffers: pinned fp noise in, result out (fp state, or NHWC uint8
@@ -402,6 +424,12 @@ class NaturalInferenceSampler:
                 noise=[torch.empty(shape, dtype=self.dtype, device=dev) for _ in range(2)],
                 out=[torch.empty(out_shape, dtype=out_dtype, device=dev) for _ in range(2)],
                 pixels=pixels, h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev), graphs={})
+            peer = self._relay_peer
+            if peer is not None:  # relay route: staging buffers and copy streams on the peer, a push stream here
+                self._stage.update(
+                    r_noise=[torch.empty(shape, dtype=self.dtype, device=peer) for _ in range(2)] if noise_hosts is not None else None,
+                    r_out=[torch.empty(out_shape, dtype=out_dtype, device=peer) for _ in range(2)],
+                    r_h2d=torch.cuda.Stream(device=peer), r_d2h=torch.cuda.Stream(device=peer), push=torch.cuda.Stream(device=dev))
         st = self._stage
         if st["pixels"] != pixels:
             raise NiError("sample_host_many was first used with a different `pixels` setting on this sampler")
@@ -415,7 +443,10 @@ class NaturalInferenceSampler:
                     nb = st["noise"][par] if noise_hosts is not None else None
                     kw = dict(pixels_out=st["out"][par]) if pixels else dict(out=st["out"][par])
                     st["graphs"][key] = (self.capture(denoiser, noise=nb, **kw), denoiser)  # keeps the denoiser alive with its graph
-        c_done, d_done = [None] * n, [None] * n
+        relay = self._relay_peer is not None
+        if relay and noise_hosts is not None and st["r_noise"] is None:
+            st["r_noise"] = [torch.empty(shape, dtype=self.dtype, device=self._relay_peer) for _ in range(2)]
+        c_done, d_done, ob_free = [None] * n, [None] * n, [None] * n
         for i in range(n):
             nb, ob = st["noise"][i % 2], st["out"][i % 2]
             if noise_hosts is not None:
@@ -427,14 +458,22 @@ class NaturalInferenceSampler:
                         st["h2d"].wait_event(c_done[i - 2])      # batch i-2 no longer reads this noise buffer
                     else:
                         st["h2d"].wait_stream(main)
-                    nb.copy_(nh, non_blocking=True)
+                    if relay:
+                        # host -> peer staging over the peer's PCIe link, then peer -> here over NVLink.  torch runs a
+                        # cross-device copy on the SOURCE device's current stream (r_h2d) after the destination device's
+                        # current stream (h2d, which holds the wait above) and makes the latter wait for it.
+                        with torch.cuda.stream(st["r_h2d"]):
+                            st["r_noise"][i % 2].copy_(nh, non_blocking=True)
+                            nb.copy_(st["r_noise"][i % 2], non_blocking=True)
+                    else:
+                        nb.copy_(nh, non_blocking=True)
                     h_done = torch.cuda.Event()
                     h_done.record(st["h2d"])
                 main.wait_event(h_done)
             else:
                 nb = None
             if i >= 2:
-                main.wait_event(d_done[i - 2])                # batch i-2's result has left this output buffer
+                main.wait_event(ob_free[i - 2])               # batch i-2's result has left this output buffer
             if graph:
                 self.replay(st["graphs"][(i % 2, noise_hosts is not None, id(denoiser))][0])
             elif pixels:
@@ -443,12 +482,27 @@ class NaturalInferenceSampler:
                 self.sample(denoiser, noise=nb, out=ob)
             c_done[i] = torch.cuda.Event()
             c_done[i].record(main)
-            with torch.cuda.stream(st["d2h"]):
-                st["d2h"].wait_event(c_done[i])
-                out_hosts[i].copy_(ob, non_blocking=True)
-                d_done[i] = torch.cuda.Event()
-                d_done[i].record(st["d2h"])
-        main.wait_stream(st["d2h"])
+            if relay:
+                with torch.cuda.stream(st["push"]):
+                    st["push"].wait_event(c_done[i])
+                    with torch.cuda.stream(st["r_d2h"]):
+                        # here -> peer staging over NVLink (runs on `push`, after the peer's earlier D2H out of that buffer),
+                        # then peer -> host over the peer's PCIe link on r_d2h
+                        st["r_out"][i % 2].copy_(ob, non_blocking=True)
+                        out_hosts[i].copy_(st["r_out"][i % 2], non_blocking=True)
+                        d_done[i] = torch.cuda.Event()
+                        d_done[i].record(st["r_d2h"])
+                    ob_free[i] = torch.cuda.Event()
+                    ob_free[i].record(st["push"])             # the output buffer is free once it has been pushed
+            else:
+                with torch.cuda.stream(st["d2h"]):
+                    st["d2h"].wait_event(c_done[i])
+                    out_hosts[i].copy_(ob, non_blocking=True)
+                    d_done[i] = torch.cuda.Event()
+                    d_done[i].record(st["d2h"])
+                ob_free[i] = d_done[i]
+        if n:
+            main.wait_event(d_done[-1])  # (also across devices: the relay's D2H runs on the peer)
         return d_done[-1] if n else None
 
 

@@ -521,3 +521,18 @@ def test_multiply_shift_sample_index_formula():
         ns = np.concatenate([np.arange(0, 2000), rng.integers(0, 1 << 31, 2000), [(1 << 31) - 1, d - 1, d, 2 * d - 1]]).astype(np.uint64)
         q = ns if mul == 0 else ((ns * np.uint64(mul)) >> np.uint64(32)) >> np.uint64(shr)
         assert np.array_equal(q, ns // np.uint64(d)), d
+
+
+def test_host_relay_pairing_from_probe_times():
+    """hostutil.relay_pairs: the measured 8-GPU box (profiles/r02_host_copy_probe_n8.json: GPUs 0-3 at ~12.2 GB/s, GPUs 4-7 at
+    ~19 GB/s with all ranks copying) pairs each far-socket rank with a near one; uniform boxes keep the direct route"""
+    from naturaldiffusion_b200.hostutil import relay_pairs
+    gbs = [12.15, 12.18, 12.14, 12.16, 19.2, 19.04, 18.94, 18.9]
+    ms = [100.0 / g for g in gbs]
+    assert relay_pairs(ms) == {0: 4, 1: 5, 2: 6, 3: 7}
+    assert relay_pairs(ms[::-1]) == {4: 0, 5: 1, 6: 2, 7: 3}
+    assert relay_pairs([1.0] * 8) is None and relay_pairs([1.0, 1.1]) is None and relay_pairs([1.0]) is None
+    assert relay_pairs([1.0, 1.0, 1.0, 2.0]) is None          # one straggler is not a slower HALF
+    assert relay_pairs([1.0, 2.0, 1.0]) is None                # odd world
+    assert relay_pairs([1.0, 2.0]) == {1: 0}
+    assert relay_pairs([1.0, 1.0], "force") == {0: 1, 1: 0}
