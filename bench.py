@@ -773,6 +773,12 @@ def run_ours(args, rank, world, local_rank):
                 ent["e2e"]["device_noise_frac_of_d2h_ceiling"] = ee["device_noise"]["frac_of_copy_ceiling"]
                 ent["e2e"]["copy_ceiling_gbs"] = ee["copy_ceiling"]["gbs_aggregate"]
                 ent["e2e"]["d2h_ceiling_gbs"] = ee["device_noise"]["copy_ceiling"]["gbs_aggregate"]
+                if "copy_ceiling_routed" in ee:  # a relay route is in use at this N (e2e.host_route)
+                    ent["e2e"]["relayed_via_gpu"] = {"host_noise": ee["host_route"]["host_noise"], "device_noise": ee["host_route"]["device_noise"]}
+                    ent["e2e"]["frac_of_copy_ceiling_routed"] = ee["frac_of_copy_ceiling_routed"]
+                    ent["e2e"]["device_noise_frac_of_d2h_ceiling_routed"] = ee["device_noise"]["frac_of_copy_ceiling_routed"]
+                    ent["e2e"]["copy_ceiling_routed_gbs"] = ee["copy_ceiling_routed"]["gbs_aggregate"]
+                    ent["e2e"]["d2h_ceiling_routed_gbs"] = ee["device_noise"]["copy_ceiling_routed"]["gbs_aggregate"]
             per[label] = ent
         line["per_config"] = per
         # C3 is the L2-clean roofline shape (201 MB tensors): quoted beside the headline
