@@ -296,8 +296,8 @@ class Ctx:
 
     def copy_ceiling_ms(self, h2d, d2h, reps, with_h2d, peer=None):
         """bare cudaMemcpyAsync of the same bytes, all ranks at once, ms per batch (max over ranks); peer = relay route"""
-        from naturaldiffusion_b200.hostutil import _CopyRig
-        rig = _CopyRig(self.dev, None if peer is None else self.torch.device("cuda", peer), h2d, d2h)
+        from naturaldiffusion_b200.hostutil import HostCopyRig
+        rig = HostCopyRig(self.dev, None if peer is None else self.torch.device("cuda", peer), h2d, d2h)
         rig.run(4, with_h2d)
         self.barrier()
         ms = rig.run(reps, with_h2d)

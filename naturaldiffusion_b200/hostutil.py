@@ -65,9 +65,9 @@ def bind_rank_cpus(local_rank: int, local_world: int) -> Optional[int]:
 # ----------------------------------------------------------------------------------------------
 # host-copy routing: which PCIe link should carry this rank's host traffic?
 # ----------------------------------------------------------------------------------------------
-class _CopyRig:
+class HostCopyRig:
     """Bare host copies of one rank, direct (this GPU's PCIe link) or relayed through an NVLink peer (the peer's link),
-    enqueued exactly like NaturalInferenceSampler.sample_host_many does.  Used only by `choose_host_relay`."""
+    enqueued exactly like NaturalInferenceSampler.sample_host_many does.  Used by `choose_host_relay` and by bench.py for its copy ceilings."""
 
     def __init__(self, dev, peer, h2d_bytes: int, d2h_bytes: int):
         import torch
@@ -176,7 +176,7 @@ def choose_host_relay(rank: int, world: int, device, h2d_bytes: int = 4096 * 307
         return gather(ms), min(gather(ok)) > 0
 
     try:
-        direct = _CopyRig(dev, None, h2d_bytes, d2h_bytes)
+        direct = HostCopyRig(dev, None, h2d_bytes, d2h_bytes)
         built = 1.0
     except Exception:  # noqa: BLE001
         direct, built = None, 0.0
@@ -201,7 +201,7 @@ def choose_host_relay(rank: int, world: int, device, h2d_bytes: int = 4096 * 307
         try:
             if not torch.cuda.can_device_access_peer(own, peer):
                 raise RuntimeError("no peer access")
-            rig = _CopyRig(dev, torch.device("cuda", peer), h2d_bytes, d2h_bytes)
+            rig = HostCopyRig(dev, torch.device("cuda", peer), h2d_bytes, d2h_bytes)
         except Exception:  # noqa: BLE001
             ok = 0.0
     if min(gather(ok)) == 0:

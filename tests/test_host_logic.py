@@ -536,3 +536,11 @@ def test_host_relay_pairing_from_probe_times():
     assert relay_pairs([1.0, 2.0, 1.0]) is None                # odd world
     assert relay_pairs([1.0, 2.0]) == {1: 0}
     assert relay_pairs([1.0, 1.0], "force") == {0: 1, 1: 0}
+
+
+def test_choose_host_relay_without_a_group_keeps_the_direct_route():
+    """world 1, mode "off", or no initialised process group: no probe, no CUDA call, direct route"""
+    from naturaldiffusion_b200.hostutil import choose_host_relay
+    for kw in (dict(rank=0, world=1, device="cuda:0"), dict(rank=0, world=8, device="cuda:0", mode="off"), dict(rank=1, world=2, device="cuda:1")):
+        peers, info = choose_host_relay(**kw)
+        assert peers == {"d2h": None, "bidir": None} and "mode" in info
