@@ -127,13 +127,18 @@ def save_weight_csv(W, sigmas, path):
             f.write(names[k] + "," + ",".join(repr(float(v)) for v in row) + "\n")
 
 
-def flow_euler_weight_table(sigmas) -> np.ndarray:
+def flow_euler_weight_table(sigmas, cliplen: int = 0, rounded: bool = True) -> np.ndarray:
     """The table of plain flow-matching Euler in the csv's own units: W[k,j] = round(100 (sigma_j - sigma_{j+1}), 2) for
     j <= k.  With the FlowMatchEuler grid this IS weights/sd3_step_28_weight.csv (every cell); `euler_weighted_sum`
-    (src/SD3NaturalInference.py:61-69) carries the same differences unrounded."""
+    (src/SD3NaturalInference.py:61-69) carries the same differences unrounded (rounded=False: W[k,j] = sigma_j - sigma_{j+1}).
+    cliplen > 0 keeps only the last `cliplen` predictions of each row, the `seq_xstarts[-cliplen:]` window of
+    `euler_weighted_sum(seq_xstarts, cliplen)` (:63, used at :118,:129,:131); 0 = the whole history, like the reference's slice."""
     sig = np.asarray(sigmas, dtype=np.float64)
-    d = np.round(100.0 * (sig[:-1] - sig[1:]), 2)
-    return np.tril(np.tile(d, (len(d), 1)))
+    d = np.round(100.0 * (sig[:-1] - sig[1:]), 2) if rounded else sig[:-1] - sig[1:]
+    W = np.tril(np.tile(d, (len(d), 1)))
+    if cliplen > 0:
+        W = W - np.tril(W, -int(cliplen))  # zero the columns j <= k - cliplen
+    return W
 
 
 def flow_match_sigmas(num_step=28, shift=3.0, num_train=1000) -> np.ndarray:

@@ -544,3 +544,30 @@ def test_choose_host_relay_without_a_group_keeps_the_direct_route():
     for kw in (dict(rank=0, world=1, device="cuda:0"), dict(rank=0, world=8, device="cuda:0", mode="off"), dict(rank=1, world=2, device="cuda:1")):
         peers, info = choose_host_relay(**kw)
         assert peers == {"d2h": None, "bidir": None} and "mode" in info
+
+
+def test_flow_euler_table_with_a_clip_window_matches_euler_weighted_sum():
+    """coeffs.flow_euler_weight_table(cliplen=c, rounded=False) -> CoeffTriple.from_sd3_table gives, row by row, the update of
+    src/SD3NaturalInference.py:129 with `euler_weighted_sum(seq_xstarts, cliplen)` (:61-69, the `[-cliplen:]` window):
+    x_{k+1} = sigma_{k+1} noise + (1 - sigma_{k+1}) * sum_window w_j x0_j / sum_window w_j  -- checked against the oracle's
+    restatement of that function on random tensors."""
+    import torch
+    from naturaldiffusion_b200.coeffs import CoeffTriple, flow_euler_weight_table, flow_match_sigmas
+    from oracle import ni_oracle as O
+    sig = flow_match_sigmas(12).astype(np.float64)
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(2, 3, 4, 4, generator=g, dtype=torch.float64) for _ in range(12)]
+    for clip in (0, 1, 3, 12, 40):
+        W = flow_euler_weight_table(sig, cliplen=clip, rounded=False)
+        for k in range(12):
+            lo = 0 if clip == 0 else max(0, k + 1 - clip)
+            assert np.all(W[k, :lo] == 0) and np.all(W[k, lo:k + 1] != 0) and np.all(W[k, k + 1:] == 0)
+        t = CoeffTriple.from_sd3_table(W, sig)
+        seq = []
+        for k in range(12):
+            seq.append([sig[k] - sig[k + 1], xs[k]])
+            ref = (1.0 - sig[k + 1]) * O.euler_weighted_sum(seq, clip)[1]
+            got = sum(t.A[k, j] * xs[j] for j in range(k + 1))
+            assert (got - ref).abs().max().item() < 1e-13 and t.B[k, 0] == sig[k + 1]
+    # the rounded, unclipped table is still the shipped csv's rule
+    assert np.array_equal(flow_euler_weight_table(sig), flow_euler_weight_table(sig, 0, True))
