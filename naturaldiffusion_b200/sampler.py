@@ -369,7 +369,12 @@ class NaturalInferenceSampler:
                 raise NiError(f"GPU {own} has no peer access to GPU {peer}")
             new = torch.device("cuda", peer)
         if new != self._relay_peer and hasattr(self, "_stage"):
-            del self._stage  # staging buffers, streams and per-buffer graphs are rebuilt for the new route
+            # staging buffers, streams and per-buffer graphs are rebuilt for the new route; copies of an earlier call may
+            # still be running on the side streams (on both devices), so drain them before the buffers go back to the allocator
+            torch.cuda.synchronize(self.device)
+            if self._relay_peer is not None:
+                torch.cuda.synchronize(self._relay_peer)
+            del self._stage
         self._relay_peer = new
 
     @torch.no_grad()
